@@ -1,0 +1,545 @@
+// kob_api.cu — implementation of the C ABI in include/kobayashi_c.h (libkobayashi_cuda.so).
+// Host side: context, HBM allocation, streams/events, strip linking (same process or CUDA IPC), launches.
+// There is NO CPU fallback: every entry point that needs the device fails with KOB_ERR_NO_DEVICE /
+// KOB_ERR_CUDA when it is missing.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/kobayashi_c.h"
+#include "kob_aux.cuh"
+#include "kob_common.cuh"
+#include "kob_fast.cuh"
+#include "kob_strict.cuh"
+
+using namespace kob;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Layout {
+    size_t elem;
+    long long pitch, rows;
+    int nfbx, nfby;
+    size_t field_bytes, off_phi[2], off_t[2], off_theta, off_flags, off_arrive, off_ticket, total;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Layout make_layout(int64_t nx, int64_t ny, int prec) {
+    Layout L;
+    L.elem = prec == KOB_F64 ? 8 : 4;
+    L.pitch = (long long)align_up((size_t)(GX + nx + GXR), 32);
+    L.rows = ny + 2 * GY;
+    L.nfbx = (int)((L.pitch + FBX - 1) / FBX);
+    L.nfby = (int)((L.rows + FBY - 1) / FBY);
+    L.field_bytes = align_up((size_t)L.pitch * (size_t)L.rows * L.elem, 256);
+    size_t o = 0;
+    L.off_phi[0] = o; o += L.field_bytes;
+    L.off_phi[1] = o; o += L.field_bytes;
+    L.off_t[0] = o; o += L.field_bytes;
+    L.off_t[1] = o; o += L.field_bytes;
+    L.off_theta = o; o += L.field_bytes;
+    L.off_flags = o; o += align_up((size_t)L.nfbx * L.nfby * 4, 256);
+    L.off_arrive = o; o += 256;
+    L.off_ticket = o; o += 256;
+    L.total = o;
+    return L;
+}
+
+struct Neighbour {
+    char* base = nullptr;   // device pointer to the neighbour's allocation (own base when unlinked)
+    long long ny = 0;
+    bool ipc = false;       // opened with cudaIpcOpenMemHandle -> must be closed
+};
+
+struct IpcBlob {            // payload of kob_ipc_handle
+    uint32_t magic, prec;
+    int64_t nx, ny, ny_global, y0;
+    cudaIpcMemHandle_t mem;
+};
+static_assert(sizeof(IpcBlob) <= sizeof(kob_ipc_handle), "kob_ipc_handle too small");
+constexpr uint32_t IPC_MAGIC = 0x4b4f4231u;  // "KOB1"
+
+}  // namespace
+
+struct kob_ctx {
+    int64_t nx = 0, ny = 0, ny_global = 0, y0 = 0;
+    int prec = KOB_F32, kernel = KOB_KERNEL_FAST, device = 0;
+    uint64_t seed = 0, step = 0;
+    uint32_t epoch = 0;
+    int cur = 0;
+    kob_params params{};
+    Layout L{};
+    char* base = nullptr;
+    float* noise_field = nullptr;
+    uint8_t* rgba = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Neighbour lower, upper;
+    bool linked = false;
+    uint64_t launches = 0;
+    int64_t frames = 0;
+    double sim_ms = 0.0;
+    std::string err;
+};
+
+namespace {
+
+int fail(kob_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define KOB_CUDA(c, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail((c), e_ == cudaErrorMemoryAllocation ? KOB_ERR_OOM : KOB_ERR_CUDA,        \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+
+template <typename real>
+StripView<real> view_of(char* base, const Layout& L, long long ny) {
+    StripView<real> v;
+    v.phi[0] = reinterpret_cast<real*>(base + L.off_phi[0]);
+    v.phi[1] = reinterpret_cast<real*>(base + L.off_phi[1]);
+    v.t[0] = reinterpret_cast<real*>(base + L.off_t[0]);
+    v.t[1] = reinterpret_cast<real*>(base + L.off_t[1]);
+    v.theta = reinterpret_cast<real*>(base + L.off_theta);
+    v.tflags = reinterpret_cast<uint32_t*>(base + L.off_flags);
+    v.arrive = reinterpret_cast<uint32_t*>(base + L.off_arrive);
+    v.ny = ny;
+    return v;
+}
+
+template <typename real>
+KParams<real> kparams_of(const kob_params& p) {
+    KParams<real> k;
+    k.dx = (real)p.dx; k.dy = (real)p.dy; k.dt = (real)p.dt; k.tau = (real)p.tau;
+    k.epsbar = (real)p.epsilon_bar; k.K = (real)p.K; k.delta = (real)p.delta; k.aniso = (real)p.anisotropy;
+    k.alpha = (real)p.alpha; k.gamma = (real)p.gamma; k.teq = (real)p.t_eq;
+    k.theta0 = (real)p.theta0; k.noise_a = (real)p.noise_a;
+    // loop invariants in the reference's own evaluation order (host arithmetic is IEEE, no contraction)
+    volatile real three_dx = (real)3.0f * k.dx;
+    k.lapden = three_dx * k.dx;
+    volatile real nebj = (-k.epsbar) * k.aniso;
+    k.neg_ebjd = nebj * k.delta;
+    k.alpha_over_pi = k.alpha / (real)REF_PI_F;
+    k.inv_dx = (real)1 / k.dx; k.inv_dy = (real)1 / k.dy; k.inv_lapden = (real)1 / k.lapden;
+    k.dt_over_tau = k.dt / k.tau;
+    const double j = p.anisotropy;
+    k.jmode = (j >= 0.0 && j <= 16.0 && std::floor(j) == j) ? (int)j : -1;
+    return k;
+}
+
+// Neighbour layouts share nx/prec with ours; only ny (hence rows) may differ, and the field offsets
+// depend on it, so views of neighbours are built from THEIR layout.
+template <typename real>
+StepArgs<real> args_of(kob_ctx* c) {
+    StepArgs<real> a;
+    a.self = view_of<real>(c->base, c->L, c->ny);
+    const Layout Ll = make_layout(c->nx, c->lower.ny, c->prec), Lu = make_layout(c->nx, c->upper.ny, c->prec);
+    a.lower = view_of<real>(c->lower.base, Ll, c->lower.ny);
+    a.upper = view_of<real>(c->upper.base, Lu, c->upper.ny);
+    a.prm = kparams_of<real>(c->params);
+    a.noise_field = c->noise_field;
+    a.seed = c->seed; a.step = c->step;
+    a.ticket = reinterpret_cast<unsigned int*>(c->base + c->L.off_ticket);
+    a.pitch = c->L.pitch; a.nx = (int)c->nx; a.ny = (int)c->ny; a.y0 = c->y0;
+    a.nfbx = c->L.nfbx; a.nfby = c->L.nfby;
+    a.cur = c->cur; a.linked = c->linked ? 1 : 0; a.epoch = c->epoch;
+    return a;
+}
+
+template <typename real>
+int launch_one_step(kob_ctx* c) {
+    StepArgs<real> a = args_of<real>(c);
+    const bool noise = c->params.noise_a != 0.0;
+    if (c->kernel == KOB_KERNEL_STRICT) {
+        constexpr int TX = 32, TY = 16;
+        dim3 block(32, 8), grid((unsigned)((c->nx + TX - 1) / TX), (unsigned)((c->ny + TY - 1) / TY));
+        if (noise) kob_step_strict<real, TX, TY, true><<<grid, block, 0, c->stream>>>(a);
+        else kob_step_strict<real, TX, TY, false><<<grid, block, 0, c->stream>>>(a);
+    } else {
+        int rc = launch_step_fast(a, noise, c->stream);
+        if (rc != KOB_OK) return fail(c, rc, "fast kernel: unsupported configuration");
+    }
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    c->cur ^= 1; c->step += 1; c->epoch += 1;
+    return KOB_OK;
+}
+
+template <typename real>
+int refresh_impl(kob_ctx* c) {
+    StepArgs<real> a = args_of<real>(c);
+    const long long items = 2LL * GY * c->nx + 2LL * GXR * c->ny;
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((items + threads - 1) / threads, 4096);
+    kob_refresh_aliases<real><<<blocks, threads, 0, c->stream>>>(a);
+    kob_publish_epoch<real><<<1, 32, 0, c->stream>>>(a);
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return KOB_OK;
+}
+
+template <typename real>
+int rebuild_flags_impl(kob_ctx* c) {
+    StepArgs<real> a = args_of<real>(c);
+    dim3 grid(c->L.nfbx, c->L.nfby);
+    kob_rebuild_flags<real><<<grid, 256, 0, c->stream>>>(a.self.theta, a.self.tflags, c->L.pitch, c->L.rows, c->L.nfbx);
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return KOB_OK;
+}
+
+template <typename real>
+int nucleus_impl(kob_ctx* c, int64_t x, int64_t y) {
+    StepArgs<real> a = args_of<real>(c);
+    kob_nucleus<real><<<1, 32, 0, c->stream>>>(a, x, y, c->ny_global);
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return KOB_OK;
+}
+
+int set_device(kob_ctx* c) {
+    KOB_CUDA(c, cudaSetDevice(c->device));
+    return KOB_OK;
+}
+
+int zero_fields(kob_ctx* c) {
+    // phi[2], T[2], theta, theta flags: one contiguous range
+    KOB_CUDA(c, cudaMemsetAsync(c->base, 0, c->L.off_arrive, c->stream));
+    return KOB_OK;
+}
+
+#define KOB_TRY(expr) do { int rc_ = (expr); if (rc_ != KOB_OK) return rc_; } while (0)
+#define KOB_DISPATCH(c, fn, ...) ((c)->prec == KOB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+bool params_ok(const kob_params* p) {
+    return p->dx > 0 && p->dy > 0 && p->dt > 0 && p->tau > 0 && std::isfinite(p->dx) && std::isfinite(p->dt) &&
+           std::isfinite(p->tau) && std::isfinite(p->anisotropy);
+}
+
+}  // namespace
+
+extern "C" {
+
+int kob_abi_version(void) { return KOB_ABI_VERSION; }
+
+const char* kob_strerror(int s) {
+    switch (s) {
+        case KOB_OK: return "ok";
+        case KOB_ERR_INVALID_ARG: return "invalid argument";
+        case KOB_ERR_CUDA: return "CUDA error";
+        case KOB_ERR_NO_DEVICE: return "no CUDA device";
+        case KOB_ERR_OOM: return "out of device memory";
+        case KOB_ERR_STATE: return "invalid state";
+        case KOB_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+const char* kob_last_error(const kob_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int kob_default_params(kob_params* p, double dt) {
+    if (!p) return KOB_ERR_INVALID_ARG;
+    p->dx = 0.03; p->dy = 0.03; p->dt = dt;                           // src/Kobayashi.cpp:61-63
+    p->tau = 0.0003; p->epsilon_bar = 0.010; p->mu = 1.0; p->K = 1.6; // :76-79
+    p->delta = 0.05; p->anisotropy = 6.0; p->alpha = 0.9; p->gamma = 10.0; p->t_eq = 1.0;  // :80-84
+    p->theta0 = 0.0; p->noise_a = 0.0;
+    return KOB_OK;
+}
+
+int kob_default_config(kob_config* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    std::memset(c, 0, sizeof(*c));
+    c->precision = KOB_F32; c->kernel = KOB_KERNEL_FAST; c->device = 0;
+    return KOB_OK;
+}
+
+int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, const kob_config* cfg) {
+    if (!out) return fail(nullptr, KOB_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    kob_params p;
+    kob_default_params(&p, 1e-4);
+    if (params) p = *params;
+    kob_config cf;
+    kob_default_config(&cf);
+    if (cfg) cf = *cfg;
+    if (nx < 2 || ny < 2 || nx > (1LL << 30) || ny > (1LL << 30))
+        return fail(nullptr, KOB_ERR_INVALID_ARG, "grid must be at least 2x2 per strip");
+    if (!params_ok(&p)) return fail(nullptr, KOB_ERR_INVALID_ARG, "dx, dy, dt, tau must be positive and finite");
+    if (cf.precision != KOB_F32 && cf.precision != KOB_F64) return fail(nullptr, KOB_ERR_INVALID_ARG, "bad precision");
+    if (cf.kernel != KOB_KERNEL_STRICT && cf.kernel != KOB_KERNEL_FAST) return fail(nullptr, KOB_ERR_INVALID_ARG, "bad kernel");
+    if (cf.kernel == KOB_KERNEL_FAST && cf.precision != KOB_F32)
+        return fail(nullptr, KOB_ERR_UNSUPPORTED, "the FAST kernel is FP32 only; use KOB_KERNEL_STRICT for FP64");
+    const int64_t nyg = cf.ny_global ? cf.ny_global : ny;
+    if (cf.y0 < 0 || cf.y0 + ny > nyg) return fail(nullptr, KOB_ERR_INVALID_ARG, "strip [y0, y0+ny) outside ny_global");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, KOB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (cf.device < 0 || cf.device >= ndev) return fail(nullptr, KOB_ERR_INVALID_ARG, "device ordinal out of range");
+
+    kob_ctx* c = new (std::nothrow) kob_ctx();
+    if (!c) return fail(nullptr, KOB_ERR_OOM, "host allocation failed");
+    c->nx = nx; c->ny = ny; c->ny_global = nyg; c->y0 = cf.y0;
+    c->prec = cf.precision; c->kernel = cf.kernel; c->device = cf.device; c->seed = cf.seed;
+    c->params = p;
+    c->L = make_layout(nx, ny, c->prec);
+    auto bail = [&](int code, const std::string& m) { g_create_error = m; kob_destroy(c); return code; };
+    cudaError_t e;
+    if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaMalloc((void**)&c->base, c->L.total)) != cudaSuccess)
+        return bail(e == cudaErrorMemoryAllocation ? KOB_ERR_OOM : KOB_ERR_CUDA,
+                    std::string("cudaMalloc(") + std::to_string(c->L.total) + "): " + cudaGetErrorString(e));
+    if ((e = cudaMemsetAsync(c->base, 0, c->L.total, c->stream)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    c->lower.base = c->base; c->lower.ny = ny;
+    c->upper.base = c->base; c->upper.ny = ny;
+    int rc = kob_reset(c);
+    if (rc != KOB_OK) return bail(rc, c->err);
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    *out = c;
+    return KOB_OK;
+}
+
+int kob_destroy(kob_ctx* c) {
+    if (!c) return KOB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->lower.ipc && c->lower.base) cudaIpcCloseMemHandle(c->lower.base);
+    if (c->upper.ipc && c->upper.base && c->upper.base != c->lower.base) cudaIpcCloseMemHandle(c->upper.base);
+    if (c->noise_field) cudaFree(c->noise_field);
+    if (c->rgba) cudaFree(c->rgba);
+    if (c->base) cudaFree(c->base);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return KOB_OK;
+}
+
+int kob_clear(kob_ctx* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    KOB_TRY(zero_fields(c));
+    c->step = 0;
+    return KOB_OK;
+}
+
+int kob_reset(kob_ctx* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(kob_clear(c));
+    c->frames = 0; c->sim_ms = 0.0;                                   // src/Kobayashi.cpp:247-248
+    return kob_add_nucleus(c, c->nx / 2, c->ny_global / 2);           // src/Kobayashi.cpp:113
+}
+
+int kob_add_nucleus(kob_ctx* c, int64_t x, int64_t y) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    return KOB_DISPATCH(c, nucleus_impl, c, x, y);
+}
+
+int kob_set_params(kob_ctx* c, const kob_params* p) {
+    if (!c || !p) return KOB_ERR_INVALID_ARG;
+    if (!params_ok(p)) return fail(c, KOB_ERR_INVALID_ARG, "dx, dy, dt, tau must be positive and finite");
+    c->params = *p;
+    return KOB_OK;
+}
+
+int kob_get_params(const kob_ctx* c, kob_params* p) {
+    if (!c || !p) return KOB_ERR_INVALID_ARG;
+    *p = c->params;
+    return KOB_OK;
+}
+
+int kob_step(kob_ctx* c, int64_t nsteps) {
+    if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    for (int64_t s = 0; s < nsteps; ++s) KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
+    return KOB_OK;
+}
+
+int kob_step_timed(kob_ctx* c, int64_t nsteps, float* ms) {
+    if (!c || !ms) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    KOB_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    KOB_TRY(kob_step(c, nsteps));
+    KOB_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    KOB_CUDA(c, cudaEventSynchronize(c->ev1));
+    KOB_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return KOB_OK;
+}
+
+int kob_update(kob_ctx* c) {
+    float ms = 0.f;
+    KOB_TRY(kob_step_timed(c, 10, &ms));                              // src/Kobayashi.cpp:230-234
+    c->sim_ms += ms; c->frames += 1;                                  // :237-238
+    return KOB_OK;
+}
+
+int kob_sync(kob_ctx* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KOB_OK;
+}
+
+int kob_get_fields(kob_ctx* c, void* phi, void* t, void* angl) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    const size_t e = c->L.elem, w = (size_t)c->nx * e, sp = (size_t)c->L.pitch * e;
+    const size_t o = ((size_t)GY * c->L.pitch + GX) * e;
+    if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(phi, w, c->base + c->L.off_phi[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
+    if (t) KOB_CUDA(c, cudaMemcpy2DAsync(t, w, c->base + c->L.off_t[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
+    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(angl, w, c->base + c->L.off_theta + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KOB_OK;
+}
+
+int kob_set_fields(kob_ctx* c, const void* phi, const void* t, const void* angl) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    const size_t e = c->L.elem, w = (size_t)c->nx * e, sp = (size_t)c->L.pitch * e;
+    const size_t o = ((size_t)GY * c->L.pitch + GX) * e;
+    if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_phi[c->cur] + o, sp, phi, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
+    if (t) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_t[c->cur] + o, sp, t, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
+    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_theta + o, sp, angl, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
+    KOB_TRY(KOB_DISPATCH(c, refresh_impl, c));
+    if (angl) KOB_TRY(KOB_DISPATCH(c, rebuild_flags_impl, c));
+    return KOB_OK;
+}
+
+int kob_set_noise_field(kob_ctx* c, const float* r) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    if (!r) {
+        if (c->noise_field) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->noise_field); c->noise_field = nullptr; }
+        return KOB_OK;
+    }
+    const size_t bytes = sizeof(float) * (size_t)c->nx * (size_t)c->ny;
+    if (!c->noise_field) KOB_CUDA(c, cudaMalloc((void**)&c->noise_field, bytes));
+    KOB_CUDA(c, cudaMemcpyAsync(c->noise_field, r, bytes, cudaMemcpyHostToDevice, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KOB_OK;
+}
+
+int kob_set_step_counter(kob_ctx* c, uint64_t s) { if (!c) return KOB_ERR_INVALID_ARG; c->step = s; return KOB_OK; }
+int kob_get_step_counter(const kob_ctx* c, uint64_t* s) { if (!c || !s) return KOB_ERR_INVALID_ARG; *s = c->step; return KOB_OK; }
+
+int kob_render_rgba(kob_ctx* c, uint8_t* rgba) {
+    if (!c || !rgba) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    const size_t bytes = 4 * (size_t)c->nx * (size_t)c->ny;
+    if (!c->rgba) KOB_CUDA(c, cudaMalloc((void**)&c->rgba, bytes));
+    dim3 block(32, 8), grid((unsigned)((c->nx + 31) / 32), (unsigned)((c->ny + 7) / 8));
+    if (c->prec == KOB_F64)
+        kob_render<double><<<grid, block, 0, c->stream>>>(reinterpret_cast<double*>(c->base + c->L.off_phi[c->cur]), c->rgba, c->L.pitch, (int)c->nx, (int)c->ny);
+    else
+        kob_render<float><<<grid, block, 0, c->stream>>>(reinterpret_cast<float*>(c->base + c->L.off_phi[c->cur]), c->rgba, c->L.pitch, (int)c->nx, (int)c->ny);
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    KOB_CUDA(c, cudaMemcpyAsync(rgba, c->rgba, bytes, cudaMemcpyDeviceToHost, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KOB_OK;
+}
+
+int kob_sim_frame(const kob_ctx* c, int64_t* f) { if (!c || !f) return KOB_ERR_INVALID_ARG; *f = c->frames; return KOB_OK; }
+int kob_sim_time_ms(const kob_ctx* c, double* ms) { if (!c || !ms) return KOB_ERR_INVALID_ARG; *ms = c->sim_ms; return KOB_OK; }
+int kob_launch_count(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->launches; return KOB_OK; }
+int kob_get_dims(const kob_ctx* c, int64_t* nx, int64_t* ny, int64_t* nyg, int64_t* y0) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    if (nx) *nx = c->nx; if (ny) *ny = c->ny; if (nyg) *nyg = c->ny_global; if (y0) *y0 = c->y0;
+    return KOB_OK;
+}
+
+int kob_host_alloc(void** p, size_t bytes) {
+    if (!p) return KOB_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return KOB_ERR_OOM; }
+    return KOB_OK;
+}
+int kob_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? KOB_OK : KOB_ERR_CUDA; }
+
+// ---- strips ------------------------------------------------------------------------------------------
+
+int kob_ipc_export(kob_ctx* c, kob_ipc_handle* out) {
+    if (!c || !out) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    IpcBlob b;
+    std::memset(&b, 0, sizeof(b));
+    b.magic = IPC_MAGIC; b.prec = (uint32_t)c->prec; b.nx = c->nx; b.ny = c->ny; b.ny_global = c->ny_global; b.y0 = c->y0;
+    KOB_CUDA(c, cudaIpcGetMemHandle(&b.mem, c->base));
+    std::memset(out, 0, sizeof(*out));
+    std::memcpy(out->bytes, &b, sizeof(b));
+    return KOB_OK;
+}
+
+static int check_neighbour(kob_ctx* c, int64_t nx, int64_t ny, int64_t nyg, int64_t y0, int prec, bool is_lower) {
+    if (nx != c->nx || prec != c->prec || nyg != c->ny_global) return fail(c, KOB_ERR_INVALID_ARG, "neighbour strip has different nx / precision / ny_global");
+    const int64_t expect = is_lower ? ((c->y0 - ny) % nyg + nyg) % nyg : (c->y0 + c->ny) % nyg;
+    if (y0 != expect) return fail(c, KOB_ERR_INVALID_ARG, is_lower ? "lower neighbour is not adjacent (y0 mismatch)" : "upper neighbour is not adjacent (y0 mismatch)");
+    if (ny < 2) return fail(c, KOB_ERR_INVALID_ARG, "neighbour strip too thin");
+    return KOB_OK;
+}
+
+int kob_ipc_link(kob_ctx* c, const kob_ipc_handle* lower, const kob_ipc_handle* upper) {
+    if (!c || !lower || !upper) return KOB_ERR_INVALID_ARG;
+    if (c->linked) return fail(c, KOB_ERR_STATE, "strip already linked");
+    KOB_TRY(set_device(c));
+    IpcBlob bl, bu;
+    std::memcpy(&bl, lower->bytes, sizeof(bl));
+    std::memcpy(&bu, upper->bytes, sizeof(bu));
+    if (bl.magic != IPC_MAGIC || bu.magic != IPC_MAGIC) return fail(c, KOB_ERR_INVALID_ARG, "not a kob_ipc_handle");
+    KOB_TRY(check_neighbour(c, bl.nx, bl.ny, bl.ny_global, bl.y0, (int)bl.prec, true));
+    KOB_TRY(check_neighbour(c, bu.nx, bu.ny, bu.ny_global, bu.y0, (int)bu.prec, false));
+    void* pl = nullptr; void* pu = nullptr;
+    KOB_CUDA(c, cudaIpcOpenMemHandle(&pl, bl.mem, cudaIpcMemLazyEnablePeerAccess));
+    const bool same = std::memcmp(&bl.mem, &bu.mem, sizeof(bl.mem)) == 0;   // P == 2: one neighbour on both sides
+    if (same) pu = pl; else KOB_CUDA(c, cudaIpcOpenMemHandle(&pu, bu.mem, cudaIpcMemLazyEnablePeerAccess));
+    c->lower.base = (char*)pl; c->lower.ny = bl.ny; c->lower.ipc = true;
+    c->upper.base = (char*)pu; c->upper.ny = bu.ny; c->upper.ipc = !same;
+    c->linked = true;
+    return KOB_OK;
+}
+
+int kob_link_local(kob_ctx* c, kob_ctx* lower, kob_ctx* upper) {
+    if (!c || !lower || !upper) return KOB_ERR_INVALID_ARG;
+    if (c->linked) return fail(c, KOB_ERR_STATE, "strip already linked");
+    KOB_TRY(check_neighbour(c, lower->nx, lower->ny, lower->ny_global, lower->y0, lower->prec, true));
+    KOB_TRY(check_neighbour(c, upper->nx, upper->ny, upper->ny_global, upper->y0, upper->prec, false));
+    KOB_TRY(set_device(c));
+    for (kob_ctx* n : {lower, upper}) {
+        if (n->device != c->device) {
+            int can = 0;
+            KOB_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, n->device));
+            if (!can) return fail(c, KOB_ERR_UNSUPPORTED, "no peer access between the strips' devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(n->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, KOB_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    c->lower.base = lower->base; c->lower.ny = lower->ny; c->lower.ipc = false;
+    c->upper.base = upper->base; c->upper.ny = upper->ny; c->upper.ipc = false;
+    c->linked = true;
+    return KOB_OK;
+}
+
+int kob_halo_refresh(kob_ctx* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    KOB_TRY(KOB_DISPATCH(c, refresh_impl, c));
+    return KOB_DISPATCH(c, rebuild_flags_impl, c);
+}
+
+}  // extern "C"

@@ -217,7 +217,9 @@ KOB_HD float noise_from_word(uint32_t w) { return (float)(w >> 8) * 5.9604644775
 KOB_HD float noise_r(uint64_t seed, uint64_t step, uint32_t i, uint32_t j) {
     const Philox4 p = philox4x32_10(i >> 2, j, (uint32_t)step, (uint32_t)(step >> 32),
                                     (uint32_t)seed, (uint32_t)(seed >> 32));
-    return noise_from_word(p.w[i & 3]);
+    const uint32_t k = i & 3u;
+    const uint32_t w = k == 0u ? p.w[0] : (k == 1u ? p.w[1] : (k == 2u ? p.w[2] : p.w[3]));
+    return noise_from_word(w);
 }
 
 }  // namespace kob
