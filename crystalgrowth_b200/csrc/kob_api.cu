@@ -388,11 +388,22 @@ int kob_update(kob_ctx* c) {
     return KOB_OK;
 }
 
+// Linked strips: did an edge tile give up waiting for a neighbour (kob_common.cuh, wait_flag)?
+static int check_fault(kob_ctx* c) {
+    if (!c->linked) return KOB_OK;
+    uint32_t fault = 0;
+    KOB_CUDA(c, cudaMemcpyAsync(&fault, c->base + c->L.off_arrive + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (fault) return fail(c, KOB_ERR_STATE, "a neighbour strip did not reach the expected step within 20 s "
+                                             "(strips must be stepped together); fields are invalid");
+    return KOB_OK;
+}
+
 int kob_sync(kob_ctx* c) {
     if (!c) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
-    return KOB_OK;
+    return check_fault(c);
 }
 
 int kob_get_fields(kob_ctx* c, void* phi, void* t, void* angl) {
@@ -404,7 +415,7 @@ int kob_get_fields(kob_ctx* c, void* phi, void* t, void* angl) {
     if (t) KOB_CUDA(c, cudaMemcpy2DAsync(t, w, c->base + c->L.off_t[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
     if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(angl, w, c->base + c->L.off_theta + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
-    return KOB_OK;
+    return check_fault(c);
 }
 
 int kob_set_fields(kob_ctx* c, const void* phi, const void* t, const void* angl) {

@@ -36,7 +36,8 @@ struct StripView {
     real* t[2];
     real* theta;
     uint32_t* tflags;   // [nfby][nfbx] : 1 = some theta in this block of the padded array may be non-zero
-    uint32_t* arrive;   // [2]: arrive[0] written by the lower neighbour, arrive[1] by the upper neighbour
+    uint32_t* arrive;   // [3]: arrive[0] written by the lower neighbour, arrive[1] by the upper neighbour,
+                        //      arrive[2] = fault word (set when a wait on a neighbour timed out)
     long long ny;       // rows owned by that strip
 };
 
@@ -147,12 +148,30 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 
 // Edge tiles wait until the neighbour whose ghost rows they read (and whose ghost rows they will write)
 // has completed `epoch` steps.  Called by all threads of the CTA.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long WAIT_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+// Bounded: a neighbour that never arrives (its process died, or strips were stepped out of order) raises the
+// strip's fault word instead of hanging the GPU; the host reports it from kob_sync / kob_get_fields.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* fault) {
+    if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(100);
+        if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { atomicExch(fault, 1u); return; }
+    }
+}
+
 template <typename real>
 __device__ __forceinline__ void wait_neighbours(const StepArgs<real>& a, bool touches_low, bool touches_high) {
     if (!a.linked) return;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        if (touches_low) while ((int)(ld_acquire_sys(&a.self.arrive[0]) - a.epoch) < 0) __nanosleep(64);
-        if (touches_high) while ((int)(ld_acquire_sys(&a.self.arrive[1]) - a.epoch) < 0) __nanosleep(64);
+        if (touches_low) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
+        if (touches_high) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
     }
     __syncthreads();
 }

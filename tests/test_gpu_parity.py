@@ -1,0 +1,349 @@
+"""GPU parity (run on the B200 box, `-m gpu`): libkobayashi_cuda.so, called through its C ABI (ctypes mirror
+class crystalgrowth_b200.Kobayashi), against the CPU oracle and the committed reference vectors.
+
+  STRICT kernel  == oracle built with the portable math provider     : BITWISE, any number of steps (G3)
+  STRICT kernel  vs reference golden vectors (libm)                   : tolerance windows of SURVEY §4 (G1/G2)
+  FAST kernel    vs reference golden vectors / libm oracle            : FP32 1e-6 single step, 1e-4 on the windows
+  full-size grids: size-independent properties (far field exactly 0, grid-size-independent sums, symmetry,
+                   shard invariance, Philox replay)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bit_equal, max_abs
+
+pytestmark = pytest.mark.gpu
+
+NUCLEI_EDGE = [(1, 1), (94, 38), (50, 0), (0, 20), (95, 39)]
+
+
+def _pair(po, cg, nx, ny, prec="f32", kernel="strict", seed=7, nuclei=None, math=None, **params):
+    p = po.default_params(**params)
+    o = po.Oracle(nx, ny, p, prec=64 if prec == "f64" else 32, math=po.MATH_PORTABLE if math is None else math,
+                  seed=seed, threads=po.lib().kobo_max_threads())
+    g = cg.Kobayashi(nx, ny, 1e-4, precision=prec, kernel=kernel, seed=seed,
+                     **{("t_eq" if k == "t_eq" else k): v for k, v in params.items()})
+    if nuclei is not None:
+        o.clear()
+        g.clear()
+        for (x, y) in nuclei:
+            o.add_nucleus(x, y)
+            g.add_nucleus(x, y)
+    return o, g
+
+
+def _assert_bitwise(o, g, what=""):
+    for name, a, b in zip(("phi", "T", "theta"), g.fields(), o.fields()):
+        assert bit_equal(a, b), f"{what}: {name} differs, max abs {max_abs(a, b)}"
+
+
+# ---------------------------------------------------------------------------------------------- STRICT
+@pytest.mark.parametrize("nx,ny,steps,prec,params,nuclei", [
+    (64, 64, 1, "f32", {}, None),
+    (64, 64, 60, "f32", {}, None),
+    (250, 250, 400, "f32", {}, None),                                   # through the FP32-chaotic regime
+    (250, 250, 400, "f32", {"anisotropy": 4.0}, None),
+    (37, 53, 200, "f32", {"anisotropy": 5.0}, [(1, 1), (35, 51), (18, 26)]),   # ragged: no tile divides it
+    (96, 40, 120, "f32", {"noise_a": 0.01}, NUCLEI_EDGE),                # nuclei on the periodic seams + Philox
+    (96, 40, 80, "f32", {"theta0": 0.3, "anisotropy": 4.0}, NUCLEI_EDGE),
+    (33, 2, 30, "f32", {}, [(5, 0), (20, 1)]),                           # thinnest legal grid in y
+    (2, 31, 30, "f32", {}, [(0, 7)]),                                    # thinnest legal grid in x
+    (300, 300, 120, "f32", {"K": 1.2, "tau": 0.0004, "delta": 0.03, "alpha": 1.1, "gamma": 15.0, "t_eq": 0.9,
+                            "epsilon_bar": 0.012, "anisotropy": 8.0}, None),
+    (64, 64, 150, "f64", {}, None),
+    (130, 70, 150, "f64", {"noise_a": 0.02}, [(0, 0), (64, 35), (129, 69)]),
+    (250, 250, 300, "f64", {"anisotropy": 4.0}, None),
+    (1024, 1024, 20, "f32", {}, None),
+])
+def test_strict_is_bitwise_equal_to_oracle(po, cg, nx, ny, steps, prec, params, nuclei):
+    o, g = _pair(po, cg, nx, ny, prec, "strict", nuclei=nuclei, **params)
+    o.step(steps)
+    g.step(steps)
+    _assert_bitwise(o, g, f"{nx}x{ny} {prec} {steps} steps")
+
+
+def test_strict_non_integer_anisotropy_and_step_by_step(po, cg):
+    o, g = _pair(po, cg, 80, 72, "f32", "strict", anisotropy=5.5)
+    for _ in range(25):
+        o.step(1)
+        g.step(1)
+        _assert_bitwise(o, g)
+
+
+def test_strict_injected_noise_field(po, cg):
+    """North star: identical noise field injected from the host -> same result as the device Philox stream."""
+    nx, ny, seed = 72, 40, 4242
+    o, g = _pair(po, cg, nx, ny, "f32", "strict", seed=seed, noise_a=0.02)
+    _, h = _pair(po, cg, nx, ny, "f32", "strict", seed=1, noise_a=0.02)
+    for s in range(6):
+        r = np.array([[po.noise_r(seed, s, i, j) for i in range(nx)] for j in range(ny)], np.float32)
+        h.set_noise_field(r)
+        h.step(1)
+        g.step(1)
+        o.step(1)
+    _assert_bitwise(o, g)
+    assert all(bit_equal(a, b) for a, b in zip(g.fields(), h.fields()))
+    h.set_noise_field(None)
+
+
+@pytest.mark.parametrize("kernel", ["strict", "fast"])
+def test_warm_windows_vs_reference_vectors_f32(po, cg, kernel):
+    """G1/G2 against vectors produced by the reference itself (glibc libm): warm start at step 500."""
+    z = np.load(os.path.join(GOLDEN, "ref_f32_n128_j6_warm.npz"), allow_pickle=True)
+    g = cg.Kobayashi(128, 128, 1e-4, precision="f32", kernel=kernel)
+    g.set_fields(z["phi_500"], z["t_500"], z["angl_500"])
+    g.step(1)
+    phi, t, th = g.fields()
+    assert max_abs(phi, z["phi_501"]) <= 1e-6 and max_abs(t, z["t_501"]) <= 1e-6     # G1
+    g.step(99)
+    assert max_abs(g.phi(), z["phi_600"]) <= 1e-4                                      # G2
+    g.step(100)
+    assert max_abs(g.phi(), z["phi_700"]) <= 1e-4 and max_abs(g.t(), z["t_700"]) <= 1e-4
+
+
+@pytest.mark.parametrize("kernel", ["strict", "fast"])
+@pytest.mark.parametrize("j", [4, 6])
+def test_cold_window_vs_reference_vectors_f32(po, cg, kernel, j):
+    """FP32 cold start: tolerance holds for N <= 6 (rounding chaos starts at sub-step 7)."""
+    z = np.load(os.path.join(GOLDEN, f"ref_f32_n64_j{j}.npz"), allow_pickle=True)
+    g = cg.Kobayashi(64, 64, 1e-4, precision="f32", kernel=kernel, anisotropy=float(j))
+    g.step(6)
+    phi, t, _ = g.fields()
+    assert max_abs(phi, z["phi_6"]) <= 1e-4 and max_abs(t, z["t_6"]) <= 1e-4
+
+
+def test_first_substeps_vs_reference_vectors_all_fields(po, cg):
+    z = np.load(os.path.join(GOLDEN, "ref_f32_n32_j6.npz"), allow_pickle=True)
+    for kernel in ("strict", "fast"):
+        g = cg.Kobayashi(32, 32, 1e-4, precision="f32", kernel=kernel)
+        for s in (1, 2, 3):
+            g.step(1)
+            phi, t, th = g.fields()
+            assert max_abs(phi, z[f"phi_{s}"]) <= 1e-6 and max_abs(t, z[f"t_{s}"]) <= 1e-6
+            assert max_abs(th, z[f"angl_{s}"]) <= 1e-5, kernel
+
+
+def test_f64_vs_reference_vectors(po, cg):
+    """FP64: 1e-10 after 300 cold steps and after +500 warm steps (BASELINE.json tolerance)."""
+    z = np.load(os.path.join(GOLDEN, "ref_f64_n64_j6.npz"), allow_pickle=True)
+    p = po.float_rounded(po.default_params())
+    g = cg.Kobayashi(64, 64, p.dt, precision="f64", params=_as_cg_params(cg, p))
+    g.step(300)
+    assert max_abs(g.phi(), z["phi_300"]) <= 1e-10 and max_abs(g.t(), z["t_300"]) <= 1e-10
+    z = np.load(os.path.join(GOLDEN, "ref_f64_n128_j6_warm.npz"), allow_pickle=True)
+    g = cg.Kobayashi(128, 128, p.dt, precision="f64", params=_as_cg_params(cg, p))
+    g.set_fields(z["phi_500"], z["t_500"], z["angl_500"])
+    g.step(1)
+    assert max_abs(g.phi(), z["phi_501"]) <= 1e-14
+    g.step(499)
+    assert max_abs(g.phi(), z["phi_1000"]) <= 1e-10 and max_abs(g.t(), z["t_1000"]) <= 1e-10
+
+
+def _as_cg_params(cg, p):
+    q = cg.KobParams()
+    for name, _ in cg.KobParams._fields_:
+        setattr(q, name, getattr(p, name))
+    return q
+
+
+# ---------------------------------------------------------------------------------------------- FAST
+@pytest.mark.parametrize("nx,ny,params,nuclei", [
+    (250, 250, {}, None),
+    (250, 250, {"anisotropy": 4.0}, None),
+    (96, 40, {"noise_a": 0.01}, NUCLEI_EDGE),
+    (37, 53, {"anisotropy": 5.0}, [(1, 1), (35, 51), (18, 26)]),
+    (33, 2, {}, [(5, 0), (20, 1)]),
+    (2, 31, {}, [(0, 7)]),
+    (200, 120, {"anisotropy": 3.0, "theta0": 0.2}, None),
+    (200, 120, {"anisotropy": 5.5}, None),                               # non-integer mode: trig path
+    (300, 300, {"K": 1.2, "tau": 0.0004, "delta": 0.03, "alpha": 1.1, "gamma": 15.0, "t_eq": 0.9,
+                "epsilon_bar": 0.012, "anisotropy": 8.0}, None),
+])
+def test_fast_single_steps_from_oracle_states(po, cg, nx, ny, params, nuclei):
+    """G1 for the roofline kernel: from identical (phi, T, theta) states along an oracle trajectory (cold AND
+    evolved), one FAST step stays within FP32 1e-6 of one reference-arithmetic step."""
+    o, g = _pair(po, cg, nx, ny, "f32", "fast", nuclei=nuclei, math=po.MATH_LIBM, **params)
+    for advance in (0, 1, 4, 45, 150):
+        o.step(advance)
+        phi, t, th = o.fields()
+        g.set_fields(phi, t, th)
+        g.step_counter = o.step_counter()
+        o.step(1)
+        g.step(1)
+        gp, gt, gth = g.fields()
+        op, ot, oth = o.fields()
+        assert max_abs(gp, op) <= 1e-6 and max_abs(gt, ot) <= 2e-6, f"after {o.step_counter()} steps"
+        # theta: identical assignment decisions; values equal up to atan rounding, modulo 2*pi at the branch cut
+        d = np.abs(gth.astype(np.float64) - oth.astype(np.float64))
+        d = np.minimum(d, np.abs(d - 2 * 3.1415926))
+        assert d.max() <= 2e-5
+
+
+def test_fast_far_field_and_symmetry(po, cg):
+    g = cg.Kobayashi(256, 256, 1e-4, kernel="fast")
+    g.step(5)
+    phi, t, th = g.fields()
+    assert (phi[:100] == 0).all() and (t[:100] == 0).all() and (th[:100] == 0).all()
+    c = 128
+    # the single nucleus is mirror symmetric about both axes for the first steps (before rounding chaos)
+    assert max_abs(phi[c - 20:c + 21, c - 20:c + 21], phi[c - 20:c + 21, c - 20:c + 21][::-1, :]) <= 1e-6
+    assert max_abs(phi[c - 20:c + 21, c - 20:c + 21], phi[c - 20:c + 21, c - 20:c + 21][:, ::-1]) <= 1e-6
+
+
+@pytest.mark.parametrize("kernel", ["strict", "fast"])
+def test_solid_cell_count_long_run(po, cg, kernel):
+    """G6: 2000 sub-steps at 250^2: solid-cell count within 2 % of the reference's 10817."""
+    g = cg.Kobayashi(250, 250, 1e-4, kernel=kernel)
+    for _ in range(200):
+        g.iUpdate()
+    phi = g.phi()
+    solid = int((phi > 0.5).sum())
+    assert abs(solid / 10817 - 1) <= 0.02, solid
+    assert g.simFrame == 200 and g.simTime > 0
+    assert np.isfinite(phi).all() and phi.min() > -0.1 and phi.max() < 1.1
+
+
+# ---------------------------------------------------------------------------------------------- full size
+@pytest.mark.parametrize("kernel", ["strict", "fast"])
+def test_4096_single_seed_grid_size_independent_sums(po, cg, kernel):
+    """C2 (4096^2, j = 4 and 6, noise off): until the crystal feels the boundary the field sums are independent
+    of the grid size, so the 4096^2 GPU run must give the 250^2 oracle sums and exact zeros far away."""
+    for j in (4.0, 6.0):
+        g = cg.Kobayashi(4096, 4096, 1e-4, kernel=kernel, anisotropy=j)
+        g.step(6)
+        phi, t, th = g.fields()
+        o = po.Oracle(250, 250, po.default_params(anisotropy=j), math=po.MATH_PORTABLE if kernel == "strict" else po.MATH_LIBM)
+        o.step(6)
+        op, ot, oth = o.fields()
+        win = (slice(2048 - 125, 2048 + 125),) * 2
+        if kernel == "strict":
+            assert bit_equal(phi[win], op) and bit_equal(t[win], ot) and bit_equal(th[win], oth)
+        else:
+            assert max_abs(phi[win], op) <= 1e-4 and max_abs(t[win], ot) <= 1e-4
+        mask = np.ones_like(phi, bool)
+        mask[win] = False
+        assert (phi[mask] == 0).all() and (t[mask] == 0).all() and (th[mask] == 0).all()
+
+
+def test_4096_f64_window_vs_oracle(po, cg):
+    """C2 FP64: 4096^2 GPU vs 250^2 oracle window, 40 steps, 1e-10 (bitwise in fact)."""
+    p = po.default_params()
+    g = cg.Kobayashi(4096, 4096, 1e-4, precision="f64")
+    g.step(40)
+    phi, t, _ = g.fields()
+    o = po.Oracle(250, 250, p, prec=64, math=po.MATH_PORTABLE, threads=po.lib().kobo_max_threads())
+    o.step(40)
+    win = (slice(2048 - 125, 2048 + 125),) * 2
+    assert max_abs(phi[win], o.fields()[0]) <= 1e-10 and max_abs(t[win], o.fields()[1]) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------- API behaviour
+def test_roundtrip_reset_params_counters(po, cg):
+    g = cg.Kobayashi(70, 50, 1e-4, kernel="strict")
+    rng = np.random.default_rng(0)
+    phi = rng.random((50, 70), np.float32)
+    t = rng.random((50, 70), np.float32)
+    th = rng.random((50, 70), np.float32)
+    g.set_fields(phi, t, th)
+    a, b, c = g.fields()
+    assert bit_equal(a, phi) and bit_equal(b, t) and bit_equal(c, th)
+    g.set_fields(phi=None, t=None, angl=None)
+    g.reset()
+    a, b, c = g.fields()
+    assert a.sum() == 5 and a[25, 35] == 1 and a[25, 34] == 1 and a[24, 35] == 1 and b.sum() == 0 and c.sum() == 0
+    g.set_params(K=1.3, reset=True)
+    assert g.K == 1.3 and g.get_params().tau == 0.0003
+    n0 = g.launch_count
+    g.step(7)
+    g.sync()
+    assert g.launch_count == n0 + 7 and g.step_counter == 7
+    g.iUpdate()
+    assert g.simFrame == 1 and g.step_counter == 17
+    g.reset()
+    assert g.simFrame == 0 and g.step_counter == 0
+
+
+def test_nucleus_wraps_like_the_oracle(po, cg):
+    o, g = _pair(po, cg, 16, 12, nuclei=[(0, 0), (15, 11), (-1, 5), (7, 12)])
+    _assert_bitwise(o, g)
+    o.step(3)
+    g.step(3)
+    _assert_bitwise(o, g)
+
+
+def test_errors_are_reported_not_thrown(po, cg):
+    with pytest.raises(cg.KobayashiError) as e:
+        cg.Kobayashi(1, 10, 1e-4)
+    assert e.value.status == -1
+    with pytest.raises(cg.KobayashiError):
+        cg.Kobayashi(32, 32, 1e-4, tau=0.0)
+    with pytest.raises(cg.KobayashiError) as e:
+        cg.Kobayashi(32, 32, 1e-4, precision="f64", kernel="fast")
+    assert e.value.status == -6
+    with pytest.raises(cg.KobayashiError):
+        cg.Kobayashi(32, 32, 1e-4, device=99)
+    g = cg.Kobayashi(32, 32, 1e-4, kernel="strict")
+    with pytest.raises(cg.KobayashiError):
+        g.step(-1)
+    with pytest.raises(ValueError):
+        g.set_fields(np.zeros((3, 3), np.float32))
+
+
+def test_render_matches_reference_colour_ramp(po, cg):
+    """kob_render_rgba vs the reference's iUpdateConstantBuffer ramp (src/Kobayashi.cpp:309-345); the expected
+    colours come from the reference TU where it is available, else from the committed ramp restatement."""
+    g = cg.Kobayashi(48, 32, 1e-4, kernel="strict")
+    rng = np.random.default_rng(1)
+    phi = rng.random((32, 48), np.float32)
+    phi[0, :4] = [0.0, 0.9, 0.99, 1.0]
+    g.set_fields(phi, None, None)
+    img = g.render_rgba()
+    p = phi.astype(np.float32)
+    c0, c1, c2, c3 = (np.array(c, np.float32) for c in ([0, 0, 0], [0.2505490, 0.5, 0.9882353], [0.3607843, 1.0, 0.9882353], [0.9005490, 1.0, 0.9882353]))
+    want = np.empty((32, 48, 3), np.float32)
+    for (lo, hi, a, b, sel) in ((0.0, 0.9, c0, c1, p <= 0.9), (0.9, 0.99, c1, c2, (p > 0.9) & (p <= 0.99)), (0.99, 1.0, c2, c3, p > 0.99)):
+        r = ((p - np.float32(lo)) * (np.float32(1.0) / (np.float32(hi) - np.float32(lo))))[..., None]
+        want[sel] = (a * (1 - r) + b * r)[sel]
+    assert np.abs(img[..., :3].astype(np.int32) - np.rint(np.clip(want, 0, 1) * 255).astype(np.int32)).max() <= 1
+    assert (img[..., 3] == 255).all()
+
+
+# ---------------------------------------------------------------------------------------------- strips on one GPU
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kernel,prec", [("strict", "f32"), ("fast", "f32"), ("strict", "f64")])
+@pytest.mark.parametrize("nstrips,nyg", [(2, 64), (3, 70), (4, 37)])
+def test_linked_strips_on_one_gpu_equal_single_domain(po, cg, kernel, prec, nstrips, nyg):
+    """G5 (shard invariance): P row strips linked with kob_link_local on ONE device — the same edge-tile peer
+    stores and step flags the multi-GPU ring uses — reproduce the single-domain run bit-for-bit."""
+    from crystalgrowth_b200.strips import partition
+    nx, steps, seed = 96, 40, 5
+    kw = dict(precision=prec, kernel=kernel, seed=seed, noise_a=0.01)
+    nuclei = [(3, 0), (48, nyg // 2), (95, nyg - 1), (20, nyg // nstrips), (70, nyg // nstrips - 1)]
+    single = cg.Kobayashi(nx, nyg, 1e-4, **kw)
+    single.clear()
+    strips = [cg.Kobayashi(nx, ny, 1e-4, ny_global=nyg, y0=y0, **kw) for (y0, ny) in partition(nyg, nstrips)]
+    for i, s in enumerate(strips):
+        s.link_local(strips[(i - 1) % nstrips], strips[(i + 1) % nstrips])
+        s.clear()
+    for (x, y) in nuclei:
+        single.add_nucleus(x, y)
+        for s in strips:
+            s.add_nucleus(x, y)
+    for s in strips:
+        s.sync()
+    for s in strips:
+        s.halo_refresh()
+    for s in strips:
+        s.sync()
+    for _ in range(steps):            # lock-step issue order: step e of every strip precedes step e+1 of any
+        for s in strips:
+            s.step(1)
+    single.step(steps)
+    want = single.fields()
+    got = [np.concatenate(parts, axis=0) for parts in zip(*[s.fields() for s in strips])]
+    for a, b in zip(got, want):
+        assert bit_equal(a, b)
+    for s in strips:
+        s.close()
