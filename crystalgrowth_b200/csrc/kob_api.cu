@@ -85,6 +85,10 @@ struct kob_ctx {
     Neighbour lower, upper;
     bool linked = false;
     uint64_t launches = 0;
+    // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
+    FastMaps maps{};
+    int fast_np = 1, fast_yj = 256;
+    unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
     std::string err;
@@ -104,6 +108,9 @@ int fail(kob_ctx* c, int code, const std::string& msg) {
             return fail((c), e_ == cudaErrorMemoryAllocation ? KOB_ERR_OOM : KOB_ERR_CUDA,        \
                         std::string(#call) + ": " + cudaGetErrorString(e_));                      \
     } while (0)
+
+#define KOB_TRY(expr) do { int rc_ = (expr); if (rc_ != KOB_OK) return rc_; } while (0)
+#define KOB_DISPATCH(c, fn, ...) ((c)->prec == KOB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 template <typename real>
 StripView<real> view_of(char* base, const Layout& L, long long ny) {
@@ -158,6 +165,100 @@ StepArgs<real> args_of(kob_ctx* c) {
     return a;
 }
 
+// ---- FAST kernel host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_fast_maps(kob_ctx* c) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+        return fail(c, KOB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+    const int bw = c->fast_np == 2 ? FastGeom<2>::BW : FastGeom<1>::BW;
+    const cuuint64_t dims[2] = {(cuuint64_t)c->L.pitch, (cuuint64_t)c->L.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->L.pitch * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)FAST_RB};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap* maps[4] = {&c->maps.phi[0], &c->maps.phi[1], &c->maps.t[0], &c->maps.t[1]};
+    const size_t offs[4] = {c->L.off_phi[0], c->L.off_phi[1], c->L.off_t[0], c->L.off_t[1]};
+    for (int i = 0; i < 4; ++i) {
+        CUresult r = enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    }
+    return KOB_OK;
+}
+
+constexpr int FAST_WARPS = 8;
+
+template <int NP, int JM, bool NOISE, bool ROT>
+int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
+    auto kern = kob_step_fast<NP, JM, NOISE, ROT>;
+    const int smem = FAST_WARPS * fast_warp_bytes<NP>() + FAST_WARPS * FAST_NST * 8;
+    static int ctas_per_sm[64] = {0};   // per device
+    int& cps = ctas_per_sm[c->device & 63];
+    if (cps == 0) {
+        KOB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, FAST_WARPS * 32, smem));
+        if (cps < 1) return fail(c, KOB_ERR_CUDA, "FAST kernel does not fit on an SM");
+    }
+    int nsm = 0;
+    KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    f.nstrips = (int)((c->nx + FastGeom<NP>::OUTC - 1) / FastGeom<NP>::OUTC);
+    f.yj = c->fast_yj;
+    f.nseg = (int)((c->ny + f.yj - 1) / f.yj);
+    const long long njobs = (long long)f.nstrips * f.nseg;
+    const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
+    f.job_base = c->job_expected;
+    kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps, a, f);
+    c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * FAST_WARPS;   // every warp overshoots once
+    return KOB_OK;
+}
+
+int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
+    const KParams<float>& P = a.prm;
+    FastArgs f{};
+    f.job_ctr = reinterpret_cast<unsigned long long*>(c->base + c->L.off_ticket + 8);
+    // eps, eps' of a cell that holds theta = 0 (far field), evaluated like src/Kobayashi.cpp:170-171
+    const double arg0 = (double)P.aniso * (0.0 - (double)P.theta0);
+    volatile float c0 = (float)std::cos(arg0), s0 = (float)std::sin(arg0);
+    volatile float dc = P.delta * c0;
+    volatile float one_dc = 1.0f + dc;
+    f.eps0 = P.epsbar * one_dc;
+    f.epsd0 = P.neg_ebjd * s0;
+    f.cj0 = (float)std::cos((double)P.aniso * (double)P.theta0);
+    f.sj0 = (float)std::sin((double)P.aniso * (double)P.theta0);
+    f.ebd = P.epsbar * P.delta;
+    f.il_dt = P.inv_lapden * P.dt;
+    f.two_pi = 2.0f * REF_PI_F;
+    f.half_pi = 0.5f * REF_PI_F;
+    const bool rot = P.theta0 != 0.0f;
+    const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
+#define KOB_FAST_CASE(NP_, JM_, ROT_)                                                          \
+    return noise ? launch_fast_t<NP_, JM_, true, ROT_>(c, a, f) : launch_fast_t<NP_, JM_, false, ROT_>(c, a, f)
+#define KOB_FAST_NP(NP_)                                                                       \
+    do {                                                                                       \
+        if (jm == 4) { KOB_FAST_CASE(NP_, 4, false); }                                         \
+        if (jm == 6) { KOB_FAST_CASE(NP_, 6, false); }                                         \
+        if (jm == 0 && !rot) { KOB_FAST_CASE(NP_, 0, false); }                                 \
+        if (jm == 0 && rot) { KOB_FAST_CASE(NP_, 0, true); }                                   \
+        KOB_FAST_CASE(NP_, -1, false);                                                         \
+    } while (0)
+    if (c->fast_np == 2) KOB_FAST_NP(2);
+    KOB_FAST_NP(1);
+#undef KOB_FAST_NP
+#undef KOB_FAST_CASE
+}
+
+template <typename real>
+int launch_fast_dispatch(kob_ctx* c, const StepArgs<real>&, bool) { return fail(c, KOB_ERR_UNSUPPORTED, "the FAST kernel is FP32 only"); }
+template <>
+int launch_fast_dispatch<float>(kob_ctx* c, const StepArgs<float>& a, bool noise) { return launch_step_fast(c, a, noise); }
+
 template <typename real>
 int launch_one_step(kob_ctx* c) {
     StepArgs<real> a = args_of<real>(c);
@@ -168,8 +269,7 @@ int launch_one_step(kob_ctx* c) {
         if (noise) kob_step_strict<real, TX, TY, true><<<grid, block, 0, c->stream>>>(a);
         else kob_step_strict<real, TX, TY, false><<<grid, block, 0, c->stream>>>(a);
     } else {
-        int rc = launch_step_fast(a, noise, c->stream);
-        if (rc != KOB_OK) return fail(c, rc, "fast kernel: unsupported configuration");
+        KOB_TRY(launch_fast_dispatch<real>(c, a, noise));
     }
     KOB_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -220,8 +320,6 @@ int zero_fields(kob_ctx* c) {
     return KOB_OK;
 }
 
-#define KOB_TRY(expr) do { int rc_ = (expr); if (rc_ != KOB_OK) return rc_; } while (0)
-#define KOB_DISPATCH(c, fn, ...) ((c)->prec == KOB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 bool params_ok(const kob_params* p) {
     return p->dx > 0 && p->dy > 0 && p->dt > 0 && p->tau > 0 && std::isfinite(p->dx) && std::isfinite(p->dt) &&
@@ -306,6 +404,13 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     if ((e = cudaMemsetAsync(c->base, 0, c->L.total, c->stream)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     c->lower.base = c->base; c->lower.ny = ny;
     c->upper.base = c->base; c->upper.ny = ny;
+    if (c->kernel == KOB_KERNEL_FAST) {
+        // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
+        if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
+        if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = std::max(4, std::atoi(e_));
+        int rcm = build_fast_maps(c);
+        if (rcm != KOB_OK) return bail(rcm, c->err);
+    }
     int rc = kob_reset(c);
     if (rc != KOB_OK) return bail(rc, c->err);
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));

@@ -45,8 +45,8 @@ if __name__ == "__main__":
     assert po.ref_available(32) and po.ref_available(64), "needs /root/reference (authoring container)"
     os.makedirs(OUT, exist_ok=True)
     run("ref_f32_n32_j6", 32, 32, [1, 2, 3])
-    run("ref_f32_n64_j6", 64, 64, [6, 10, 100])
-    run("ref_f32_n64_j4", 64, 64, [6, 10, 100], anisotropy=4.0)
+    run("ref_f32_n64_j6", 64, 64, [4, 6, 10, 100])
+    run("ref_f32_n64_j4", 64, 64, [4, 6, 10, 100], anisotropy=4.0)
     run("ref_f64_n64_j6", 64, 64, [10, 100, 300], prec=64)
     run("ref_f64_n64_j4", 64, 64, [10, 100, 300], prec=64, anisotropy=4.0)
     # ragged grid, several nuclei touching the periodic seams (kept >= 1 cell inside: the reference's

@@ -106,12 +106,15 @@ def test_warm_windows_vs_reference_vectors_f32(po, cg, kernel):
 @pytest.mark.parametrize("kernel", ["strict", "fast"])
 @pytest.mark.parametrize("j", [4, 6])
 def test_cold_window_vs_reference_vectors_f32(po, cg, kernel, j):
-    """FP32 cold start: tolerance holds for N <= 6 (rounding chaos starts at sub-step 7)."""
+    """FP32 cold start: the nucleus-centre cell has a mathematically zero gradient, so its angle is decided by
+    rounding noise against the FLT_EPSILON dead-band; with glibc libm that first flips phi by ~8e-3 at sub-step 7
+    (SURVEY §5.7), with any other atan/sin/cos (portable provider, CUDA libm) it can flip at sub-step 6.  The
+    tolerance window that every rounding-level variant satisfies is therefore N <= 4-5; N = 4 is tested."""
     z = np.load(os.path.join(GOLDEN, f"ref_f32_n64_j{j}.npz"), allow_pickle=True)
     g = cg.Kobayashi(64, 64, 1e-4, precision="f32", kernel=kernel, anisotropy=float(j))
-    g.step(6)
+    g.step(4)
     phi, t, _ = g.fields()
-    assert max_abs(phi, z["phi_6"]) <= 1e-4 and max_abs(t, z["t_6"]) <= 1e-4
+    assert max_abs(phi, z["phi_4"]) <= 1e-6 and max_abs(t, z["t_4"]) <= 1e-6
 
 
 def test_first_substeps_vs_reference_vectors_all_fields(po, cg):
@@ -212,10 +215,10 @@ def test_4096_single_seed_grid_size_independent_sums(po, cg, kernel):
     of the grid size, so the 4096^2 GPU run must give the 250^2 oracle sums and exact zeros far away."""
     for j in (4.0, 6.0):
         g = cg.Kobayashi(4096, 4096, 1e-4, kernel=kernel, anisotropy=j)
-        g.step(6)
+        g.step(4)
         phi, t, th = g.fields()
         o = po.Oracle(250, 250, po.default_params(anisotropy=j), math=po.MATH_PORTABLE if kernel == "strict" else po.MATH_LIBM)
-        o.step(6)
+        o.step(4)
         op, ot, oth = o.fields()
         win = (slice(2048 - 125, 2048 + 125),) * 2
         if kernel == "strict":
@@ -347,3 +350,36 @@ def test_linked_strips_on_one_gpu_equal_single_domain(po, cg, kernel, prec, nstr
         assert bit_equal(a, b)
     for s in strips:
         s.close()
+
+
+# ---------------------------------------------------------------------------------------------- FAST variants
+@pytest.mark.parametrize("np_,yj", [(1, 8), (2, 256), (2, 12), (1, 5)])
+def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj):
+    """The FAST kernel's decomposition knobs (cells per lane, rows per job) do not change results: every variant
+    passes the single-step gate, and the job height is bit-neutral."""
+    def run(env_np, env_yj, nx=150, ny=90, steps=12):
+        monkeypatch.setenv("KOB_FAST_NP", str(env_np))
+        monkeypatch.setenv("KOB_FAST_YJ", str(env_yj))
+        g = cg.Kobayashi(nx, ny, 1e-4, kernel="fast", seed=9, noise_a=0.01)
+        g.clear()
+        for (x, y) in [(0, 0), (75, 45), (149, 89), (30, 7), (120, 8)]:
+            g.add_nucleus(x, y)
+        g.step(steps)
+        return g
+    a = run(np_, yj).fields()
+    b = run(np_, 256).fields()
+    assert all(bit_equal(x, y) for x, y in zip(a, b))
+    # single-step gate from an evolved oracle state
+    o = po.Oracle(150, 90, po.default_params(noise_a=0.01), math=po.MATH_LIBM, seed=9)
+    o.clear()
+    for (x, y) in [(0, 0), (75, 45), (149, 89), (30, 7), (120, 8)]:
+        o.add_nucleus(x, y)
+    o.step(30)
+    monkeypatch.setenv("KOB_FAST_NP", str(np_))
+    monkeypatch.setenv("KOB_FAST_YJ", str(yj))
+    g = cg.Kobayashi(150, 90, 1e-4, kernel="fast", seed=9, noise_a=0.01)
+    g.set_fields(*o.fields())
+    g.step_counter = o.step_counter()
+    o.step(1)
+    g.step(1)
+    assert max_abs(g.phi(), o.fields()[0]) <= 1e-6 and max_abs(g.t(), o.fields()[1]) <= 2e-6
