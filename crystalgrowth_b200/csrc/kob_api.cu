@@ -87,7 +87,7 @@ struct kob_ctx {
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
     FastMaps maps{};
-    int fast_np = 1, fast_yj = 256;
+    int fast_np = 1, fast_yj = 64;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;

@@ -80,13 +80,12 @@ template <typename real>
 __device__ __forceinline__ void store_aliases(real* __restrict__ self_buf, real* lower_buf, real* upper_buf,
                                               long long pitch, int nx, int ny, long long ny_lower, int i, int j,
                                               real v) {
-    int xs[3];
-    int n = 0;
-    xs[n++] = i;
-    if (i < GXR) xs[n++] = i + nx;
-    if (i >= nx - GXR) xs[n++] = i - nx;
-    for (int k = 0; k < n; ++k) {
-        const int x = xs[k];
+    // x aliases: the cell itself, its right-hand ghost copy (columns 0..GXR-1 -> nx..), its left-hand ghost copy
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k == 1 && !(i < GXR)) continue;
+        if (k == 2 && !(i >= nx - GXR)) continue;
+        const int x = k == 0 ? i : (k == 1 ? i + nx : i - nx);
         self_buf[pidx<real>(pitch, x, j)] = v;
         if (j < GY) lower_buf[(long long)(ny_lower + j + GY) * pitch + (x + GX)] = v;
         if (j >= ny - GY) upper_buf[(long long)(j - ny + GY) * pitch + (x + GX)] = v;

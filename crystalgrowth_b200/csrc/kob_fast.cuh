@@ -25,6 +25,8 @@
 
 #include <cuda.h>   // CUtensorMap (type only; the encode entry point is fetched at run time, no -lcuda)
 
+#include <type_traits>
+
 #include "kob_common.cuh"
 
 namespace kob {
@@ -114,10 +116,51 @@ __device__ __forceinline__ void cpow_rt(int j, float c, float s, float& C, float
     C = rc; S = rs;
 }
 
+// ---- packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two cells per issue slot) -----------------
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+    return r;
+}
+// component k (compile-time) of an array of cell pairs
+#define KOB_CX(arr, k) (((k) & 1) ? (arr)[(k) >> 1].y : (arr)[(k) >> 1].x)
+
+// ---- rare paths, kept out of line so that the steady-state row loop stays small in the instruction cache ----
+__device__ __noinline__ void fast_sincos(float arg, float* s, float* c) { sincosf(arg, s, c); }
+// Store to every alias of an owned seam cell (own ghost columns, neighbour strips' ghost rows).
+__device__ __noinline__ void fast_store_edge(float* self_buf, float* lower_buf, float* upper_buf, long long pitch, int nx,
+                                             int ny, long long ny_lower, int i, int j, float v) {
+    store_aliases<float>(self_buf, lower_buf, upper_buf, pitch, nx, ny, ny_lower, i, j, v);
+}
+__device__ __noinline__ void fast_mark_flags(uint32_t* self_f, uint32_t* lower_f, uint32_t* upper_f, long long ny_lower,
+                                             long long ny_upper, int nx, int ny, int nfbx, int nfby, int x0, int y0,
+                                             int tx, int ty) {
+    StepArgs<float> a;
+    a.self.tflags = self_f; a.lower.tflags = lower_f; a.upper.tflags = upper_f;
+    a.lower.ny = ny_lower; a.upper.ny = ny_upper; a.nx = nx; a.ny = ny; a.nfbx = nfbx; a.nfby = nfby;
+    mark_tile_flags<float>(a, x0, y0, tx, ty);
+}
+
+// Reference angle of a re-assigned cell (src/Kobayashi.cpp:154-167); gy/gx by reciprocal (2 ulp) — theta only
+// feeds cos/sin(j*theta) of later HELD steps, a rounding-level difference.
+__device__ __forceinline__ float fast_theta_value(float gx, float gy, bool flat, float pi, float two_pi, float half_pi) {
+    const float at = atanf(__fdividef(gy, gx));
+    const float th = gx > 0.f ? (gy < 0.f ? two_pi + at : at) : pi + at;
+    return flat ? (gy < 0.f ? -half_pi : half_pi) : th;
+}
+
 // JM: 4 / 6 = compile-time integer mode, 0 = run-time integer mode (prm.jmode in 0..16), -1 = any real j (trig).
 template <int NP, int JM, bool NOISE, bool ROT>
-__global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ FastMaps maps,
-                                                         const StepArgs<float> a, const FastArgs f) {
+__global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
+                                                         const FastArgs f) {
     using G = FastGeom<NP>;
     constexpr int CPL = G::CPL, BW = G::BW, RB = FAST_RB, NST = FAST_NST;
     constexpr int STAGE_FLOATS = fast_stage_floats<NP>(), BOX_FLOATS = fast_box_floats<NP>();
@@ -141,7 +184,8 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
     const long long pitch = a.pitch;
     const float e = REF_DEADBAND, pi = REF_PI_F;
     const int njobs = f.nstrips * f.nseg;
-    unsigned int gchunk = 0;   // chunks issued/consumed so far by this warp: stage = gchunk % NST, parity = (gchunk / NST) & 1
+    const float A0 = f.eps0 * f.eps0, B0 = f.eps0 * f.epsd0;
+    unsigned int gchunk = 0;   // chunks consumed so far by this warp: stage = gchunk % NST, parity = (gchunk / NST) & 1
 
     for (;;) {
         unsigned long long jraw = 0;
@@ -153,9 +197,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
         const int y0 = seg * f.yj, y1 = min(y0 + f.yj, a.ny);
         const int xs = strip * G::OUTC - CPL;            // first pass-1 column of the warp (lane 0, halo)
         const int x = xs + CPL * lane;                   // first cell of this lane
-        const bool out_lane = lane >= 1 && lane <= 30 && x < a.nx;
-        const bool vec_ok = x + CPL <= a.nx;
-        const bool edge_lane = x < GXR || x + CPL > a.nx - GXR;
+        const bool mid_lane = lane >= 1 && lane <= 30;
 
         if (a.linked) {
             if (lane == 0) {
@@ -174,12 +216,14 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             for (int k = lane; k < nb; k += 32) fl |= __ldcg(&a.self.tflags[(by0 + k / nbx) * a.nfbx + bx0 + k % nbx]);
             live = __any_sync(0xffffffffu, fl != 0u);
         }
+        // seam job: touches the first/last GXR columns or GY rows -> alias stores, ragged right edge
+        const bool seam = strip == 0 || (strip + 1) * G::OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
 
         const int nrows = (y1 - y0) + 4;                 // streamed phi rows y0-2 .. y1+1
         const int nch = (nrows + RB - 1) / RB;
         const int box_x = xs - CPL + GX;                 // padded x of box column 0
-        auto issue = [&](int c) {                        // lane 0: chunk c of this job -> stage (gchunk_issue % NST)
-            const unsigned int gi = gchunk + (unsigned int)c;   // gchunk = global index of this job's chunk 0
+        auto issue = [&](int c) {                        // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
+            const unsigned int gi = gchunk + (unsigned int)c;
             const int st = gi % NST;
             float* dst = stages + st * STAGE_FLOATS;
             mbar_expect_tx(&bars[st], 2 * RB * BW * 4);
@@ -191,85 +235,102 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             for (int c = 0; c < NST && c < nch; ++c) issue(c);
         }
 
-        // ---- register state (per cell c of this lane) ----
-        float po0[CPL], po1[CPL];          // phi rows r-2, r-1
-        float gx1[CPL];                    // gx of row r-1 (pass 1 pending), then row r-2 (pass 2)
-        float gx2[CPL], gy2[CPL];          // gx, gy of row r-2
-        float u1[CPL], lp1[CPL];           // u(r-1), partial lap (r-1)
-        float lap2[CPL];                   // lap phi (r-2) complete
-        float tq1[CPL], tu1[CPL], tlp1[CPL];   // T: own (r-2), u (r-2), partial lap (r-2)   [T lags one row]
-        float A1[CPL], A2[CPL], A3[CPL];   // eps^2 rows r-1 (new), r-2, r-3
-        float P1[CPL], P3[CPL], P2[CPL];   // eps*eps'*gx rows r-1, r-2, r-3
-        float Q2[CPL];                     // eps*eps'*gy row r-2
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            po0[c] = po1[c] = gx1[c] = gx2[c] = gy2[c] = u1[c] = lp1[c] = lap2[c] = 0.f;
-            tq1[c] = tu1[c] = tlp1[c] = 0.f;
-            A1[c] = A2[c] = A3[c] = P1[c] = P2[c] = P3[c] = Q2[c] = 0.f;
-        }
         bool assigned_any = false;
 
-        for (int c = 0; c < nch; ++c) {
-            const unsigned int gi = gchunk + (unsigned int)c;
-            const int st = gi % NST;
-            mbar_wait(&bars[st], (gi / NST) & 1u);
-            const float* sp = stages + st * STAGE_FLOATS;          // phi rows
-            const float* stt = sp + BOX_FLOATS;                     // T rows (one row behind)
+        // The row loop, instantiated twice: GEN = false is the lean steady-state path (interior strip, no theta
+        // to read, no seams); GEN = true additionally reads held theta, handles the ragged edge and the aliases.
+        auto body = [&](auto gen_tag) {
+            constexpr bool GEN = decltype(gen_tag)::value;
+            // register windows, one float2 per pair of adjacent cells; "r" is the phi row streamed in this iteration
+            float2 po0[NP], po1[NP];               // phi rows r-2, r-1
+            float2 gx1[NP], gx2[NP], gy2[NP];      // gx(r-1); gx, gy (r-2)
+            float2 u1[NP], lp1[NP], lap2[NP];      // u(r-1), c(r-1)+u(r-2), complete 9-point sum of row r-2
+            float2 tq1[NP], tu1[NP], tlp1[NP];     // T(r-2), u_T(r-2), c_T(r-2)+u_T(r-3)        [T lags phi by a row]
+            float2 A2[NP], A3[NP];                 // eps^2 rows r-2, r-3
+            float2 P2[NP], P3[NP];                 // eps*eps'*gx rows r-2, r-3
+            float2 Q2[NP];                         // eps*eps'*gy row r-2
 #pragma unroll
-            for (int rr = 0; rr < RB; ++rr) {
-                const int r = y0 - 2 + c * RB + rr;                // phi row streamed in this iteration
-                if (r > y1 + 1) break;
-                // ---- phi row r ----
-                float pn[CPL], hsum[CPL], gxn[CPL];
-                {
-                    const float* row = sp + rr * BW + CPL * lane + CPL;
-                    float w = row[-1], ee = row[CPL];
-                    if (NP == 1) { const float2 v = *reinterpret_cast<const float2*>(row); pn[0] = v.x; pn[1] = v.y; }
-                    else { const float4 v = *reinterpret_cast<const float4*>(row); pn[0] = v.x; pn[1] = v.y; pn[2 % CPL] = v.z; pn[3 % CPL] = v.w; }
+            for (int p = 0; p < NP; ++p) {
+                po0[p] = po1[p] = gx1[p] = gx2[p] = gy2[p] = u1[p] = lp1[p] = lap2[p] = f2(0.f);
+                tq1[p] = tu1[p] = tlp1[p] = f2(0.f);
+                A2[p] = A3[p] = P2[p] = P3[p] = Q2[p] = f2(0.f);
+            }
+            // running pointers to cell (x, r-2) of the output arrays / theta
+            long long o2 = pidx<float>(pitch, x, y0 - 4);
+            float* pphi = phi_out + o2;
+            float* ptt = t_out + o2;
+            const unsigned int nvalid = (unsigned int)(y1 - y0);
+            const unsigned int nstore = mid_lane ? nvalid : 0u;    // rows this lane stores
+            const float2 idx2 = f2(P.inv_dx), idy2 = f2(P.inv_dy), il2 = f2(P.inv_lapden), ildt2 = f2(f.il_dt);
+            const float2 dtt2 = f2(P.dt_over_tau), K2 = f2(P.K), two2 = f2(2.0f), m12 = f2(-12.0f), B02 = f2(B0);
+
+            for (int c = 0; c < nch; ++c) {
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                mbar_wait(&bars[st], (gi / NST) & 1u);
+                const float* sp = stages + st * STAGE_FLOATS + CPL * lane + CPL;   // this lane's own phi cells
+                const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
+                const int yrel0 = c * RB - 4;                                       // (r - 2) - y0 for rr = 0
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float l = k == 0 ? w : pn[k - 1], rgt = k == CPL - 1 ? ee : pn[k + 1];
-                        hsum[k] = l + rgt;
-                        gxn[k] = (rgt - l) * P.inv_dx;
-                    }
-                }
-                // ---- pass 1 for row r-1 (needs phi rows r-2, r-1, r) ----
-                float An[CPL], Pn[CPL], Qn[CPL], gyn[CPL];
-                if (r >= y0) {
-                    const int y = r - 1;
-                    bool asg[CPL];
-                    bool any_asg = false;
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        gyn[k] = (pn[k] - po0[k]) * P.inv_dy;
-                        asg[k] = (gx1[k] < -e) || (fabsf(gyn[k]) > e);
-                        any_asg |= asg[k];
-                    }
-                    float th_old[CPL];
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) th_old[k] = 0.f;
-                    if (live) {   // warp-uniform
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k)
-                            if (!asg[k] && x + k < a.nx + GXR && x + k >= -GXR) th_old[k] = __ldg(&a.self.theta[pidx<float>(pitch, x + k, y)]);
-                    }
-                    if (!__any_sync(0xffffffffu, any_asg) && !live) {
-                        // far field: every cell holds theta = 0
+                for (int rr = 0; rr < RB; ++rr) {
+                    const unsigned int yrel = (unsigned int)(yrel0 + rr);           // row of pass 2, relative to y0
+                    // ---- phi row r: own cells, horizontal sums and x-gradient ----
+                    float2 pn[NP], hsum[NP], gxn[NP];
+                    {
+                        const float* row = sp + rr * BW;
+                        const float w = row[-1], ee = row[CPL];
+                        if (NP == 1) pn[0] = *reinterpret_cast<const float2*>(row);
+                        else { const float4 v = *reinterpret_cast<const float4*>(row); pn[0] = make_float2(v.x, v.y); pn[NP - 1] = make_float2(v.z, v.w); }
+                        float2 gxd[NP];
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
-                            An[k] = f.eps0 * f.eps0;
-                            const float B = f.eps0 * f.epsd0;
-                            Pn[k] = B * gx1[k];
-                            Qn[k] = B * gyn[k];
+                            const float l = k == 0 ? w : KOB_CX(pn, k - 1), rgt = k == CPL - 1 ? ee : KOB_CX(pn, k + 1);
+                            KOB_CX(hsum, k) = l + rgt;
+                            KOB_CX(gxd, k) = rgt - l;
                         }
-                    } else {
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) gxn[p] = f2mul(gxd[p], idx2);           // :139
+                    }
+                    // ---- pass 1 for row r-1 (phi rows r-2, r-1, r) ----
+                    float2 An[NP], Pn[NP], Qn[NP], gyn[NP];
+                    {
+                        bool asg[CPL];
+                        bool any_asg = false;
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) gyn[p] = f2mul(f2sub(pn[p], po0[p]), idy2);   // :140
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
-                            const float gx = gx1[k], gy = gyn[k];
-                            float C, S;
-                            if (asg[k]) {
-                                const bool flat = (gx <= e) && (gx >= -e);                  // case A (:154-158)
-                                float th;
+                            asg[k] = (KOB_CX(gx1, k) < -e) || (fabsf(KOB_CX(gyn, k)) > e);          // :154-167: re-assigned
+                            any_asg |= asg[k];
+                        }
+                        float th_old[CPL];
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) th_old[k] = 0.f;
+                        bool busy = __any_sync(0xffffffffu, any_asg);
+                        if (GEN) {
+                            if (live) {   // warp-uniform: held cells keep their last angle
+                                bool nz = false;
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k) {
+                                    if (!asg[k] && x + k < a.nx + GXR && x + k >= -GXR && yrel + 2u <= nvalid + 1u)
+                                        th_old[k] = __ldg(&a.self.theta[o2 + pitch + k]);
+                                    nz |= th_old[k] != 0.f;
+                                }
+                                busy |= __any_sync(0xffffffffu, nz);
+                            }
+                        }
+                        if (!busy) {
+                            // far field: every cell of the warp row holds theta = 0
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) { An[p] = f2(A0); Pn[p] = f2mul(B02, gx1[p]); Qn[p] = f2mul(B02, gyn[p]); }
+                        } else {
+                            const int y = y0 + (int)yrel + 1;
+                            const bool row_owned = yrel + 1u < nvalid;
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                const float gx = KOB_CX(gx1, k), gy = KOB_CX(gyn, k);
+                                const bool flat = (gx <= e) && (gx >= -e);                   // case A (:154-158)
+                                float C = 1.0f, S = 0.0f;
                                 if (JM >= 0) {
                                     const float rinv = rsqrtf(fmaf(gx, gx, gy * gy));
                                     const float c1 = flat ? 0.0f : gx * rinv;
@@ -277,152 +338,174 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                     if (JM == 0) cpow_rt(P.jmode, c1, s1, C, S); else cpow<JM>(c1, s1, C, S);
                                     if (ROT) { const float c2 = fmaf(C, f.cj0, S * f.sj0), s2 = fmaf(S, f.cj0, -C * f.sj0); C = c2; S = s2; }
                                 }
-                                const bool owned = out_lane && y >= y0 && y < y1 && x + k < a.nx;
-                                if (JM < 0 || owned) {
-                                    if (flat) th = gy < 0.f ? -f.half_pi : f.half_pi;
-                                    else {
-                                        const float at = atanf(__fdiv_rn(gy, gx));
-                                        th = gx > 0.f ? (gy < 0.f ? f.two_pi + at : at) : pi + at;     // :160-167
-                                    }
-                                    if (JM < 0) sincosf(P.aniso * (th - P.theta0), &S, &C);
-                                    if (owned) {
-                                        store_aliases<float>(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny,
-                                                             a.lower.ny, x + k, y, th);
-                                        assigned_any = true;
+                                const bool owned = asg[k] && row_owned && mid_lane && (!GEN || x + k < a.nx);
+                                if (JM < 0) {
+                                    if (asg[k]) {
+                                        const float th = fast_theta_value(gx, gy, flat, pi, f.two_pi, f.half_pi);
+                                        fast_sincos(P.aniso * (th - P.theta0), &S, &C);
                                     }
                                 }
-                            } else if (th_old[k] != 0.f) {
-                                sincosf(P.aniso * (th_old[k] - P.theta0), &S, &C);          // held, non-zero angle (rare)
-                            } else {
-                                C = 1.0f; S = 0.f;                                           // unused: eps0 / epsd0 below
-                            }
-                            const bool zero_hold = !asg[k] && th_old[k] == 0.f;
-                            const float ep = zero_hold ? f.eps0 : fmaf(f.ebd, C, P.epsbar);                // :170
-                            const float ed = zero_hold ? f.epsd0 : P.neg_ebjd * S;                          // :171
-                            An[k] = ep * ep;
-                            const float B = ep * ed;
-                            Pn[k] = B * gx;
-                            Qn[k] = B * gy;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) { An[k] = Pn[k] = Qn[k] = gyn[k] = 0.f; }
-                }
-                // ---- T row r-1: own cells + horizontal neighbours ----
-                float tn[CPL], thsum[CPL];
-                {
-                    const float* row = stt + rr * BW + CPL * lane + CPL;
-                    float w = row[-1], ee = row[CPL];
-                    if (NP == 1) { const float2 v = *reinterpret_cast<const float2*>(row); tn[0] = v.x; tn[1] = v.y; }
-                    else { const float4 v = *reinterpret_cast<const float4*>(row); tn[0] = v.x; tn[1] = v.y; tn[2 % CPL] = v.z; tn[3 % CPL] = v.w; }
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float l = k == 0 ? w : tn[k - 1], rgt = k == CPL - 1 ? ee : tn[k + 1];
-                        thsum[k] = l + rgt;
-                    }
-                }
-                // ---- pass 2 for row r-2 ----
-                if (r >= y0 + 2 && r - 2 < y1) {
-                    const int y = r - 2;
-                    // horizontal neighbours of the pass-1 products of row y (A2, Q2) from the adjacent lanes
-                    const float A_w = __shfl_up_sync(0xffffffffu, A2[CPL - 1], 1);
-                    const float A_e = __shfl_down_sync(0xffffffffu, A2[0], 1);
-                    const float Q_w = __shfl_up_sync(0xffffffffu, Q2[CPL - 1], 1);
-                    const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0], 1);
-                    float np_[CPL], nt_[CPL], q[CPL];
-                    bool any_q = false;
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) { q[k] = fmaf(-po0[k], po0[k], po0[k]); any_q |= (q[k] != 0.f); }
-                    // note: at this point po0 = phi(r-2) = phi(y), po1 = phi(r-1)
-                    const bool active = __any_sync(0xffffffffu, any_q);
-                    float rq[4];
-                    if (NOISE && active) {
-                        if (a.noise_field) {
-#pragma unroll
-                            for (int k = 0; k < CPL; ++k)
-                                rq[k] = (q[k] != 0.f && x + k >= 0 && x + k < a.nx) ? __ldg(&a.noise_field[(long long)(x + k) + (long long)a.nx * y]) : 0.5f;
-                        } else {
-                            const Philox4 ph = philox4x32_10((uint32_t)x >> 2, (uint32_t)(a.y0 + y), (uint32_t)a.step,
-                                                             (uint32_t)(a.step >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                            if (NP == 2) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) rq[k] = noise_from_word(ph.w[k]);
-                            } else {
-                                const bool hi = (x & 2) != 0;
-                                rq[0] = noise_from_word(hi ? ph.w[2] : ph.w[0]);
-                                rq[1] = noise_from_word(hi ? ph.w[3] : ph.w[1]);
+                                if (owned) {
+                                    const float th = fast_theta_value(gx, gy, flat, pi, f.two_pi, f.half_pi);
+                                    if (GEN && (y < GY || y >= a.ny - GY || x + k < GXR || x + k >= a.nx - GXR))
+                                        fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
+                                    else
+                                        a.self.theta[o2 + pitch + k] = th;
+                                    assigned_any = true;
+                                }
+                                float ep = fmaf(f.ebd, C, P.epsbar);                         // :170
+                                float ed = P.neg_ebjd * S;                                   // :171
+                                if (GEN) {
+                                    if (!asg[k] && th_old[k] != 0.f) {                       // held, non-zero angle (rare)
+                                        fast_sincos(P.aniso * (th_old[k] - P.theta0), &S, &C);
+                                        ep = fmaf(f.ebd, C, P.epsbar);
+                                        ed = P.neg_ebjd * S;
+                                    } else if (!asg[k]) { ep = f.eps0; ed = f.epsd0; }
+                                } else if (!asg[k]) { ep = f.eps0; ed = f.epsd0; }
+                                KOB_CX(An, k) = ep * ep;
+                                const float B = ep * ed;
+                                KOB_CX(Pn, k) = B * gx;
+                                KOB_CX(Qn, k) = B * gy;
                             }
                         }
                     }
+                    // ---- T row r-1: own cells + horizontal sums ----
+                    float2 tn[NP], thsum[NP];
+                    {
+                        const float* row = stt + rr * BW;
+                        const float w = row[-1], ee = row[CPL];
+                        if (NP == 1) tn[0] = *reinterpret_cast<const float2*>(row);
+                        else { const float4 v = *reinterpret_cast<const float4*>(row); tn[0] = make_float2(v.x, v.y); tn[NP - 1] = make_float2(v.z, v.w); }
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float Aw = k == 0 ? A_w : A2[k - 1], Ae = k == CPL - 1 ? A_e : A2[k + 1];
-                        const float Qw = k == 0 ? Q_w : Q2[k - 1], Qe = k == CPL - 1 ? Q_e : Q2[k + 1];
-                        const float gEx = (Ae - Aw) * P.inv_dx;                               // :190-192
-                        const float gEy = (An[k] - A3[k]) * P.inv_dy;                         // :193-195
-                        const float t1 = (Pn[k] - P3[k]) * P.inv_dy;                          // :197-199
-                        float sum = fmaf(-(Qe - Qw), P.inv_dx, t1);                           // + term2, :201-203
-                        sum = fmaf(A2[k], lap2[k] * P.inv_lapden, sum);                       // eps^2 * lap(phi)
-                        sum = fmaf(gEx, gx2[k], sum);                                         // term3, :204
-                        sum = fmaf(gEy, gy2[k], sum);
-                        const float op = po0[k], ot = tq1[k];
+                        for (int k = 0; k < CPL; ++k) {
+                            const float l = k == 0 ? w : KOB_CX(tn, k - 1), rgt = k == CPL - 1 ? ee : KOB_CX(tn, k + 1);
+                            KOB_CX(thsum, k) = l + rgt;
+                        }
+                    }
+                    // ---- pass 2 for row y = r-2 (computed unconditionally; stores predicated on the row being owned) ----
+                    float2 tu_new[NP];
+                    {
+                        const float A_w = __shfl_up_sync(0xffffffffu, A2[NP - 1].y, 1);
+                        const float A_e = __shfl_down_sync(0xffffffffu, A2[0].x, 1);
+                        const float Q_w = __shfl_up_sync(0xffffffffu, Q2[NP - 1].y, 1);
+                        const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0].x, 1);
+                        float2 q[NP], dA[NP], dQ[NP], sum[NP], np_[NP], nt_[NP];
+                        bool any_q = false;
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            q[p] = f2fma(make_float2(-po0[p].x, -po0[p].y), po0[p], po0[p]);   // phi (1 - phi)
+                            any_q |= (q[p].x != 0.f) || (q[p].y != 0.f);
+                        }
+                        const bool active = __any_sync(0xffffffffu, any_q);
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            const float Aw = k == 0 ? A_w : KOB_CX(A2, k - 1), Ae = k == CPL - 1 ? A_e : KOB_CX(A2, k + 1);
+                            const float Qw = k == 0 ? Q_w : KOB_CX(Q2, k - 1), Qe = k == CPL - 1 ? Q_e : KOB_CX(Q2, k + 1);
+                            KOB_CX(dA, k) = Ae - Aw;                                         // :190-192
+                            KOB_CX(dQ, k) = Qw - Qe;                                         // term2, :201-203
+                        }
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            const float2 gEx = f2mul(dA[p], idx2);
+                            const float2 gEy = f2mul(f2sub(An[p], A3[p]), idy2);             // :193-195
+                            const float2 t1 = f2mul(f2sub(Pn[p], P3[p]), idy2);              // :197-199
+                            float2 sm = f2fma(dQ[p], idx2, t1);
+                            sm = f2fma(A2[p], f2mul(lap2[p], il2), sm);                      // eps^2 * lap(phi)
+                            sm = f2fma(gEx, gx2[p], sm);                                     // term3, :204
+                            sum[p] = f2fma(gEy, gy2[p], sm);
+                        }
                         if (active) {
-                            const float m = P.alpha_over_pi * atanf(P.gamma * (P.teq - ot));  // :206
-                            sum = fmaf(q[k], (op - 0.5f) + m, sum);                           // :214
-                            if (NOISE) sum = fmaf(P.noise_a * q[k], rq[k] - 0.5f, sum);
-                        }
-                        np_[k] = fmaf(sum, P.dt_over_tau, op);                                // :211
-                        const float lapt = tlp1[k] + fmaf(2.0f, tn[k], thsum[k]);              // lap T (y) * 3dx^2
-                        nt_[k] = fmaf(P.K, np_[k] - op, fmaf(lapt, f.il_dt, ot));             // :215
-                    }
-                    if (out_lane) {
-                        const bool edge_row = y < GY || y >= a.ny - GY;
-                        if (vec_ok && !edge_row && !edge_lane) {
-                            const long long o = pidx<float>(pitch, x, y);
-                            if (NP == 1) {
-                                *reinterpret_cast<float2*>(phi_out + o) = make_float2(np_[0], np_[1]);
-                                *reinterpret_cast<float2*>(t_out + o) = make_float2(nt_[0], nt_[1]);
-                            } else {
-                                *reinterpret_cast<float4*>(phi_out + o) = make_float4(np_[0], np_[1], np_[2 % CPL], np_[3 % CPL]);
-                                *reinterpret_cast<float4*>(t_out + o) = make_float4(nt_[0], nt_[1], nt_[2 % CPL], nt_[3 % CPL]);
-                            }
-                        } else {
+                            float rq[4];
+                            if (NOISE) {
+                                const int y = y0 + (int)yrel;
+                                if (a.noise_field) {
 #pragma unroll
-                            for (int k = 0; k < CPL; ++k)
-                                if (x + k < a.nx) {
-                                    store_aliases<float>(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, np_[k]);
-                                    store_aliases<float>(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, nt_[k]);
+                                    for (int k = 0; k < CPL; ++k)
+                                        rq[k] = (KOB_CX(q, k) != 0.f && x + k >= 0 && x + k < a.nx && yrel < nvalid)
+                                                    ? __ldg(&a.noise_field[(long long)(x + k) + (long long)a.nx * y]) : 0.5f;
+                                } else {
+                                    const Philox4 ph = philox4x32_10((uint32_t)x >> 2, (uint32_t)(a.y0 + y), (uint32_t)a.step,
+                                                                     (uint32_t)(a.step >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                                    if (NP == 2) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) rq[k] = noise_from_word(ph.w[k]);
+                                    } else {
+                                        const bool hi = (x & 2) != 0;
+                                        rq[0] = noise_from_word(hi ? ph.w[2] : ph.w[0]);
+                                        rq[1] = noise_from_word(hi ? ph.w[3] : ph.w[1]);
+                                    }
                                 }
+                            }
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                const float m = P.alpha_over_pi * atanf(P.gamma * (P.teq - KOB_CX(tq1, k)));    // :206
+                                float radd = KOB_CX(q, k) * ((KOB_CX(po0, k) - 0.5f) + m);                       // :214
+                                if (NOISE) radd = fmaf(P.noise_a * KOB_CX(q, k), rq[k] - 0.5f, radd);
+                                KOB_CX(sum, k) += radd;
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            np_[p] = f2fma(sum[p], dtt2, po0[p]);                            // :211
+                            tu_new[p] = f2fma(two2, tn[p], thsum[p]);                        // u_T(r-1)
+                            const float2 lapt = f2add(tlp1[p], tu_new[p]);                   // 9-point sum of T at row y
+                            nt_[p] = f2fma(K2, f2sub(np_[p], po0[p]), f2fma(lapt, ildt2, tq1[p]));   // :215
+                        }
+                        if (yrel < nstore) {
+                            if (!GEN) {
+                                if (NP == 1) {
+                                    *reinterpret_cast<float2*>(pphi) = np_[0];
+                                    *reinterpret_cast<float2*>(ptt) = nt_[0];
+                                } else {
+                                    *reinterpret_cast<float4*>(pphi) = make_float4(np_[0].x, np_[0].y, np_[NP - 1].x, np_[NP - 1].y);
+                                    *reinterpret_cast<float4*>(ptt) = make_float4(nt_[0].x, nt_[0].y, nt_[NP - 1].x, nt_[NP - 1].y);
+                                }
+                            } else {
+                                const int y = y0 + (int)yrel;
+                                const bool edge = y < GY || y >= a.ny - GY || x < GXR || x + CPL > a.nx - GXR;
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k)
+                                    if (x + k < a.nx) {
+                                        if (edge) {
+                                            fast_store_edge(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, KOB_CX(np_, k));
+                                            fast_store_edge(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, KOB_CX(nt_, k));
+                                        } else {
+                                            pphi[k] = KOB_CX(np_, k);
+                                            ptt[k] = KOB_CX(nt_, k);
+                                        }
+                                    }
+                            }
                         }
                     }
-                }
-                // ---- rotate the register windows ----
+                    // ---- rotate the register windows ----
+                    o2 += pitch;
+                    pphi += pitch;
+                    ptt += pitch;
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    // T (row r-1 becomes "r-2" of the next iteration)
-                    const float tu_new = fmaf(2.0f, tn[k], thsum[k]);                        // u_T(r-1)
-                    tlp1[k] = fmaf(2.0f, thsum[k], fmaf(-12.0f, tn[k], tu1[k]));             // c_T(r-1) + u_T(r-2)
-                    tu1[k] = tu_new;
-                    tq1[k] = tn[k];
-                    // phi
-                    const float u_new = fmaf(2.0f, pn[k], hsum[k]);                          // u(r)
-                    lap2[k] = lp1[k] + u_new;                                                // lap(r-1) complete
-                    lp1[k] = fmaf(2.0f, hsum[k], fmaf(-12.0f, pn[k], u1[k]));                // c(r) + u(r-1)
-                    u1[k] = u_new;
-                    gx2[k] = gx1[k]; gy2[k] = gyn[k]; gx1[k] = gxn[k];
-                    po0[k] = po1[k]; po1[k] = pn[k];
-                    A3[k] = A2[k]; A2[k] = An[k];
-                    P3[k] = P2[k]; P2[k] = Pn[k];
-                    Q2[k] = Qn[k];
+                    for (int p = 0; p < NP; ++p) {
+                        tlp1[p] = f2fma(two2, thsum[p], f2fma(m12, tn[p], tu1[p]));          // c_T(r-1) + u_T(r-2)
+                        tu1[p] = tu_new[p];
+                        tq1[p] = tn[p];
+                        const float2 u_new = f2fma(two2, pn[p], hsum[p]);                    // u(r)
+                        lap2[p] = f2add(lp1[p], u_new);                                      // 9-point sum of row r-1 complete
+                        lp1[p] = f2fma(two2, hsum[p], f2fma(m12, pn[p], u1[p]));             // c(r) + u(r-1)
+                        u1[p] = u_new;
+                        gx2[p] = gx1[p]; gy2[p] = gyn[p]; gx1[p] = gxn[p];
+                        po0[p] = po1[p]; po1[p] = pn[p];
+                        A3[p] = A2[p]; A2[p] = An[p];
+                        P3[p] = P2[p]; P2[p] = Pn[p];
+                        Q2[p] = Qn[p];
+                    }
                 }
+                __syncwarp();
+                if (lane == 0 && c + NST < nch) issue(c + NST);
             }
-            __syncwarp();
-            if (lane == 0 && c + NST < nch) issue(c + NST);
-        }
+        };
+        if (live || seam) body(std::true_type{}); else body(std::false_type{});
+
         gchunk += (unsigned int)nch;
-        if (__any_sync(0xffffffffu, assigned_any) && lane == 0)
-            mark_tile_flags(a, max(strip * G::OUTC, 0), y0, G::OUTC, y1 - y0);
+        if (__any_sync(0xffffffffu, assigned_any) && lane == 0) fast_mark_flags(a.self.tflags, a.lower.tflags, a.upper.tflags, a.lower.ny, a.upper.ny, a.nx, a.ny, a.nfbx, a.nfby,
+                            strip * G::OUTC, y0, G::OUTC, y1 - y0);
     }
     signal_neighbours(a);
 }
