@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libkobayashi_cuda.so")
+# KOB_LIB_PATH: development knob to load an alternative build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("KOB_LIB_PATH") or os.path.join(PKG, "libkobayashi_cuda.so")
 
 KOB_F32, KOB_F64 = 0, 1
 KOB_KERNEL_STRICT, KOB_KERNEL_FAST = 0, 1

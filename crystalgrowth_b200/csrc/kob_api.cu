@@ -87,7 +87,9 @@ struct kob_ctx {
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
     FastMaps maps{};
-    int fast_np = 1, fast_yj = 64;
+    int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
+    double fast_frac_a = 0.9;
+    int fast_cta_jobs = 0;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
@@ -209,9 +211,16 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     int nsm = 0;
     KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     f.nstrips = (int)((c->nx + FastGeom<NP>::OUTC - 1) / FastGeom<NP>::OUTC);
+    // guided job heights: fast_yj rows for the first fast_frac_a of the strip, fast_yj_b rows for the rest
     f.yj = c->fast_yj;
-    f.nseg = (int)((c->ny + f.yj - 1) / f.yj);
-    const long long njobs = (long long)f.nstrips * f.nseg;
+    f.yj_b = std::min(c->fast_yj_b, c->fast_yj);
+    f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
+    if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
+    const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
+    f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
+    f.cta_jobs = c->fast_cta_jobs;
+    f.nstrips_p = (f.nstrips + FAST_WARPS - 1) / FAST_WARPS * FAST_WARPS;
+    const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
     f.job_base = c->job_expected;
     kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps, a, f);
@@ -407,7 +416,10 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     if (c->kernel == KOB_KERNEL_FAST) {
         // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
         if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
-        if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));
         int rcm = build_fast_maps(c);
         if (rcm != KOB_OK) return bail(rcm, c->err);
     }

@@ -39,7 +39,11 @@ struct FastMaps {
 struct FastArgs {
     unsigned long long* job_ctr;   // monotonically increasing across launches
     unsigned long long job_base;   // counter value at which this launch's job 0 sits
-    int nstrips, nseg, yj;         // jobs = nstrips x nseg; rows per segment
+    // jobs = nstrips x nseg.  Row segments: nseg_a segments of yj rows, then segments of yj_b rows up to ny
+    // (guided scheduling: big jobs first, small jobs last, so that the tail of the dynamic queue is short).
+    int nstrips, nseg, yj, nseg_a, yj_b;
+    int cta_jobs;                  // 1: a CTA claims 8 adjacent strips of one segment and keeps its warps in lock-step
+    int nstrips_p;                 // strips padded to a multiple of the warps per CTA (cta_jobs only)
     // constants of the far field / held-with-theta==0 cells: eps and eps' at theta = 0
     float eps0, epsd0;
     float cj0, sj0;                // cos(j*theta0), sin(j*theta0) for the theta0 rotation
@@ -56,8 +60,14 @@ struct FastGeom {
     static constexpr int BW = WCOLS + 2 * CPL;    // TMA box width (own cells of lane L at box column CPL*L + CPL)
 };
 
-constexpr int FAST_RB = 4;     // rows per TMA chunk
-constexpr int FAST_NST = 4;    // stages per warp
+#ifndef KOB_FAST_RB
+#define KOB_FAST_RB 4
+#endif
+#ifndef KOB_FAST_NST
+#define KOB_FAST_NST 4
+#endif
+constexpr int FAST_RB = KOB_FAST_RB;     // rows per TMA chunk (= unroll of the row loop)
+constexpr int FAST_NST = KOB_FAST_NST;   // TMA stages per warp
 
 // one stage = phi box + T box, each padded to a multiple of 128 bytes (TMA shared-memory destination alignment)
 template <int NP>
@@ -183,18 +193,32 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
     float* __restrict__ t_out = a.self.t[a.cur ^ 1];
     const long long pitch = a.pitch;
     const float e = REF_DEADBAND, pi = REF_PI_F;
-    const int njobs = f.nstrips * f.nseg;
     const float A0 = f.eps0 * f.eps0, B0 = f.eps0 * f.epsd0;
     unsigned int gchunk = 0;   // chunks consumed so far by this warp: stage = gchunk % NST, parity = (gchunk / NST) & 1
 
+    __shared__ unsigned long long s_job;
+    const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
+    const int njobs_q = nsp * f.nseg;
     for (;;) {
         unsigned long long jraw = 0;
-        if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
-        jraw = __shfl_sync(0xffffffffu, jraw, 0);
-        if (jraw >= (unsigned long long)njobs) break;
+        if (f.cta_jobs) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+            __syncthreads();
+            jraw = s_job + (unsigned long long)warp;
+            if (s_job >= (unsigned long long)njobs_q) break;
+        } else {
+            if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
+            jraw = __shfl_sync(0xffffffffu, jraw, 0);
+            if (jraw >= (unsigned long long)njobs_q) break;
+        }
         const int job = (int)jraw;
-        const int seg = job / f.nstrips, strip = job - seg * f.nstrips;
-        const int y0 = seg * f.yj, y1 = min(y0 + f.yj, a.ny);
+        const int strip = job - (job / nsp) * nsp;
+        // queue order: the two segments on the torus seam first (they take the slower generic path), small ones last
+        const int sq = job / nsp;
+        const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);
+        const int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
+        const int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
         const int xs = strip * G::OUTC - CPL;            // first pass-1 column of the warp (lane 0, halo)
         const int x = xs + CPL * lane;                   // first cell of this lane
         const bool mid_lane = lane >= 1 && lane <= 30;
@@ -206,21 +230,31 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             }
             __syncwarp();
         }
-        // theta may be non-zero somewhere in the pass-1 footprint of this job?
-        bool live;
+        // theta may be non-zero somewhere in the pass-1 footprint of this job?  One bit per 32-row flag row.
+        uint32_t livemask = 0;
+        const int fby0 = max((y0 - 1 + GY) / FBY, 0);
         {
             const int bx0 = max((xs + GX) / FBX, 0), bx1 = min((xs + GX + G::WCOLS - 1) / FBX, a.nfbx - 1);
-            const int by0 = max((y0 - 1 + GY) / FBY, 0), by1 = min((y1 + GY) / FBY, a.nfby - 1);
-            const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
-            uint32_t fl = 0;
-            for (int k = lane; k < nb; k += 32) fl |= __ldcg(&a.self.tflags[(by0 + k / nbx) * a.nfbx + bx0 + k % nbx]);
-            live = __any_sync(0xffffffffu, fl != 0u);
+            const int by1 = min((y1 + GY) / FBY, a.nfby - 1);
+            const int nbx = bx1 - bx0 + 1, nby = by1 - fby0 + 1;
+            for (int i0 = 0; i0 < nby; i0 += 32) {       // lane i looks at flag row fby0 + i0 + i
+                uint32_t fl = 0;
+                if (i0 + lane < nby)
+                    for (int bx = 0; bx < nbx; ++bx) fl |= __ldcg(&a.self.tflags[(fby0 + i0 + lane) * a.nfbx + bx0 + bx]);
+                const uint32_t m = __ballot_sync(0xffffffffu, fl != 0u);
+                livemask |= i0 == 0 ? m : (m ? 0x80000000u : 0u);   // flag rows beyond 31 fold into the last bit
+            }
         }
+        const bool live = livemask != 0u;
         // seam job: touches the first/last GXR columns or GY rows -> alias stores, ragged right edge
         const bool seam = strip == 0 || (strip + 1) * G::OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
 
         const int nrows = (y1 - y0) + 4;                 // streamed phi rows y0-2 .. y1+1
         const int nch = (nrows + RB - 1) / RB;
+        if (strip >= f.nstrips) {                        // padding job (cta_jobs): only keep the CTA's barriers company
+            for (int c = 0; c < nch; ++c) __syncthreads();
+            continue;
+        }
         const int box_x = xs - CPL + GX;                 // padded x of box column 0
         auto issue = [&](int c) {                        // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
             const unsigned int gi = gchunk + (unsigned int)c;
@@ -255,6 +289,10 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                 tq1[p] = tu1[p] = tlp1[p] = f2(0.f);
                 A2[p] = A3[p] = P2[p] = P3[p] = Q2[p] = f2(0.f);
             }
+            // GEN: theta of the held cells, prefetched two rows ahead: thp0 = theta(r-1), thp1 = theta(r)
+            float thp0[CPL], thp1[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) thp0[k] = thp1[k] = 0.f;
             // running pointers to cell (x, r-2) of the output arrays / theta
             long long o2 = pidx<float>(pitch, x, y0 - 4);
             float* pphi = phi_out + o2;
@@ -267,6 +305,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             for (int c = 0; c < nch; ++c) {
                 const unsigned int gi = gchunk + (unsigned int)c;
                 const int st = gi % NST;
+                if (f.cta_jobs) __syncthreads();                                    // adjacent strips advance together
                 mbar_wait(&bars[st], (gi / NST) & 1u);
                 const float* sp = stages + st * STAGE_FLOATS + CPL * lane + CPL;   // this lane's own phi cells
                 const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
@@ -291,39 +330,50 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 #pragma unroll
                         for (int p = 0; p < NP; ++p) gxn[p] = f2mul(gxd[p], idx2);           // :139
                     }
-                    // ---- pass 1 for row r-1 (phi rows r-2, r-1, r) ----
-                    float2 An[NP], Pn[NP], Qn[NP], gyn[NP];
+                    // ---- T row r-1: own cells + horizontal sums ----
+                    float2 tn[NP], thsum[NP];
                     {
-                        bool asg[CPL];
-                        bool any_asg = false;
-#pragma unroll
-                        for (int p = 0; p < NP; ++p) gyn[p] = f2mul(f2sub(pn[p], po0[p]), idy2);   // :140
+                        const float* row = stt + rr * BW;
+                        const float w = row[-1], ee = row[CPL];
+                        if (NP == 1) tn[0] = *reinterpret_cast<const float2*>(row);
+                        else { const float4 v = *reinterpret_cast<const float4*>(row); tn[0] = make_float2(v.x, v.y); tn[NP - 1] = make_float2(v.z, v.w); }
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
-                            asg[k] = (KOB_CX(gx1, k) < -e) || (fabsf(KOB_CX(gyn, k)) > e);          // :154-167: re-assigned
-                            any_asg |= asg[k];
+                            const float l = k == 0 ? w : KOB_CX(tn, k - 1), rgt = k == CPL - 1 ? ee : KOB_CX(tn, k + 1);
+                            KOB_CX(thsum, k) = l + rgt;
                         }
+                    }
+                    // ---- pass 1 for row r-1 (phi rows r-2, r-1, r), far-field values first ----
+                    float2 An[NP], Pn[NP], Qn[NP], gyn[NP], q[NP], radd[NP];
+                    bool asg[CPL];
+                    bool interesting = false;        // some cell re-assigns its angle (pass 1) or has phi(1-phi) != 0 (pass 2)
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        gyn[p] = f2mul(f2sub(pn[p], po0[p]), idy2);                          // :140
+                        An[p] = f2(A0); Pn[p] = f2mul(B02, gx1[p]); Qn[p] = f2mul(B02, gyn[p]);   // cells holding theta = 0
+                        q[p] = f2fma(make_float2(-po0[p].x, -po0[p].y), po0[p], po0[p]);     // phi (1 - phi) of row r-2
+                        radd[p] = f2(0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        asg[k] = (KOB_CX(gx1, k) < -e) || (fabsf(KOB_CX(gyn, k)) > e);      // :154-167: theta re-assigned
+                        interesting |= asg[k] || (KOB_CX(q, k) != 0.f);
+                    }
+                    if (GEN) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) interesting |= thp0[k] != 0.f;       // a held cell may carry an angle
+                    }
+                    // ONE vote per row; everything data dependent lives in this cold block
+                    if (__any_sync(0xffffffffu, interesting)) {
+                        bool any_asg = false, any_q = false;
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) { any_asg |= asg[k]; any_q |= KOB_CX(q, k) != 0.f; }
                         float th_old[CPL];
+                        bool nz = false;
 #pragma unroll
-                        for (int k = 0; k < CPL; ++k) th_old[k] = 0.f;
-                        bool busy = __any_sync(0xffffffffu, any_asg);
-                        if (GEN) {
-                            if (live) {   // warp-uniform: held cells keep their last angle
-                                bool nz = false;
-#pragma unroll
-                                for (int k = 0; k < CPL; ++k) {
-                                    if (!asg[k] && x + k < a.nx + GXR && x + k >= -GXR && yrel + 2u <= nvalid + 1u)
-                                        th_old[k] = __ldg(&a.self.theta[o2 + pitch + k]);
-                                    nz |= th_old[k] != 0.f;
-                                }
-                                busy |= __any_sync(0xffffffffu, nz);
-                            }
-                        }
-                        if (!busy) {
-                            // far field: every cell of the warp row holds theta = 0
-#pragma unroll
-                            for (int p = 0; p < NP; ++p) { An[p] = f2(A0); Pn[p] = f2mul(B02, gx1[p]); Qn[p] = f2mul(B02, gyn[p]); }
-                        } else {
+                        for (int k = 0; k < CPL; ++k) { th_old[k] = (GEN && !asg[k]) ? thp0[k] : 0.f; nz |= th_old[k] != 0.f; }
+                        const bool busy = __any_sync(0xffffffffu, any_asg || nz);
+                        if (busy) {
                             const int y = y0 + (int)yrel + 1;
                             const bool row_owned = yrel + 1u < nvalid;
 #pragma unroll
@@ -347,10 +397,16 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                 }
                                 if (owned) {
                                     const float th = fast_theta_value(gx, gy, flat, pi, f.two_pi, f.half_pi);
-                                    if (GEN && (y < GY || y >= a.ny - GY || x + k < GXR || x + k >= a.nx - GXR))
+                                    if (GEN && (y < GY || y >= a.ny - GY))
                                         fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
-                                    else
-                                        a.self.theta[o2 + pitch + k] = th;
+                                    else {
+                                        float* pth = a.self.theta + (o2 + pitch + k);
+                                        *pth = th;
+                                        if (GEN) {
+                                            if (x + k < GXR) pth[a.nx] = th;
+                                            if (x + k >= a.nx - GXR) pth[-a.nx] = th;
+                                        }
+                                    }
                                     assigned_any = true;
                                 }
                                 float ep = fmaf(f.ebd, C, P.epsbar);                         // :170
@@ -368,53 +424,8 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                 KOB_CX(Qn, k) = B * gy;
                             }
                         }
-                    }
-                    // ---- T row r-1: own cells + horizontal sums ----
-                    float2 tn[NP], thsum[NP];
-                    {
-                        const float* row = stt + rr * BW;
-                        const float w = row[-1], ee = row[CPL];
-                        if (NP == 1) tn[0] = *reinterpret_cast<const float2*>(row);
-                        else { const float4 v = *reinterpret_cast<const float4*>(row); tn[0] = make_float2(v.x, v.y); tn[NP - 1] = make_float2(v.z, v.w); }
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) {
-                            const float l = k == 0 ? w : KOB_CX(tn, k - 1), rgt = k == CPL - 1 ? ee : KOB_CX(tn, k + 1);
-                            KOB_CX(thsum, k) = l + rgt;
-                        }
-                    }
-                    // ---- pass 2 for row y = r-2 (computed unconditionally; stores predicated on the row being owned) ----
-                    float2 tu_new[NP];
-                    {
-                        const float A_w = __shfl_up_sync(0xffffffffu, A2[NP - 1].y, 1);
-                        const float A_e = __shfl_down_sync(0xffffffffu, A2[0].x, 1);
-                        const float Q_w = __shfl_up_sync(0xffffffffu, Q2[NP - 1].y, 1);
-                        const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0].x, 1);
-                        float2 q[NP], dA[NP], dQ[NP], sum[NP], np_[NP], nt_[NP];
-                        bool any_q = false;
-#pragma unroll
-                        for (int p = 0; p < NP; ++p) {
-                            q[p] = f2fma(make_float2(-po0[p].x, -po0[p].y), po0[p], po0[p]);   // phi (1 - phi)
-                            any_q |= (q[p].x != 0.f) || (q[p].y != 0.f);
-                        }
-                        const bool active = __any_sync(0xffffffffu, any_q);
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) {
-                            const float Aw = k == 0 ? A_w : KOB_CX(A2, k - 1), Ae = k == CPL - 1 ? A_e : KOB_CX(A2, k + 1);
-                            const float Qw = k == 0 ? Q_w : KOB_CX(Q2, k - 1), Qe = k == CPL - 1 ? Q_e : KOB_CX(Q2, k + 1);
-                            KOB_CX(dA, k) = Ae - Aw;                                         // :190-192
-                            KOB_CX(dQ, k) = Qw - Qe;                                         // term2, :201-203
-                        }
-#pragma unroll
-                        for (int p = 0; p < NP; ++p) {
-                            const float2 gEx = f2mul(dA[p], idx2);
-                            const float2 gEy = f2mul(f2sub(An[p], A3[p]), idy2);             // :193-195
-                            const float2 t1 = f2mul(f2sub(Pn[p], P3[p]), idy2);              // :197-199
-                            float2 sm = f2fma(dQ[p], idx2, t1);
-                            sm = f2fma(A2[p], f2mul(lap2[p], il2), sm);                      // eps^2 * lap(phi)
-                            sm = f2fma(gEx, gx2[p], sm);                                     // term3, :204
-                            sum[p] = f2fma(gEy, gy2[p], sm);
-                        }
-                        if (active) {
+                        if (__any_sync(0xffffffffu, any_q)) {
+                            // reaction term q*((phi - 1/2) + m(T)) [+ noise] of row r-2, :206-214
                             float rq[4];
                             if (NOISE) {
                                 const int y = y0 + (int)yrel;
@@ -439,14 +450,37 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
                                 const float m = P.alpha_over_pi * atanf(P.gamma * (P.teq - KOB_CX(tq1, k)));    // :206
-                                float radd = KOB_CX(q, k) * ((KOB_CX(po0, k) - 0.5f) + m);                       // :214
-                                if (NOISE) radd = fmaf(P.noise_a * KOB_CX(q, k), rq[k] - 0.5f, radd);
-                                KOB_CX(sum, k) += radd;
+                                float rv = KOB_CX(q, k) * ((KOB_CX(po0, k) - 0.5f) + m);                         // :214
+                                if (NOISE) rv = fmaf(P.noise_a * KOB_CX(q, k), rq[k] - 0.5f, rv);
+                                KOB_CX(radd, k) = rv;
                             }
+                        }
+                    }
+                    // ---- pass 2 for row y = r-2 (computed unconditionally; stores predicated on the row being owned) ----
+                    float2 tu_new[NP];
+                    {
+                        const float A_w = __shfl_up_sync(0xffffffffu, A2[NP - 1].y, 1);
+                        const float A_e = __shfl_down_sync(0xffffffffu, A2[0].x, 1);
+                        const float Q_w = __shfl_up_sync(0xffffffffu, Q2[NP - 1].y, 1);
+                        const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0].x, 1);
+                        float2 dA[NP], dQ[NP], np_[NP], nt_[NP];
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            const float Aw = k == 0 ? A_w : KOB_CX(A2, k - 1), Ae = k == CPL - 1 ? A_e : KOB_CX(A2, k + 1);
+                            const float Qw = k == 0 ? Q_w : KOB_CX(Q2, k - 1), Qe = k == CPL - 1 ? Q_e : KOB_CX(Q2, k + 1);
+                            KOB_CX(dA, k) = Ae - Aw;                                         // :190-192
+                            KOB_CX(dQ, k) = Qw - Qe;                                         // term2, :201-203
                         }
 #pragma unroll
                         for (int p = 0; p < NP; ++p) {
-                            np_[p] = f2fma(sum[p], dtt2, po0[p]);                            // :211
+                            const float2 gEx = f2mul(dA[p], idx2);
+                            const float2 gEy = f2mul(f2sub(An[p], A3[p]), idy2);             // :193-195
+                            float2 sm = f2fma(f2sub(Pn[p], P3[p]), idy2, radd[p]);           // term1 (:197-199) + reaction
+                            sm = f2fma(dQ[p], idx2, sm);
+                            sm = f2fma(A2[p], f2mul(lap2[p], il2), sm);                      // eps^2 * lap(phi)
+                            sm = f2fma(gEx, gx2[p], sm);                                     // term3, :204
+                            sm = f2fma(gEy, gy2[p], sm);
+                            np_[p] = f2fma(sm, dtt2, po0[p]);                                // :211
                             tu_new[p] = f2fma(two2, tn[p], thsum[p]);                        // u_T(r-1)
                             const float2 lapt = f2add(tlp1[p], tu_new[p]);                   // 9-point sum of T at row y
                             nt_[p] = f2fma(K2, f2sub(np_[p], po0[p]), f2fma(lapt, ildt2, tq1[p]));   // :215
@@ -462,18 +496,38 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                 }
                             } else {
                                 const int y = y0 + (int)yrel;
-                                const bool edge = y < GY || y >= a.ny - GY || x < GXR || x + CPL > a.nx - GXR;
+                                if (y < GY || y >= a.ny - GY) {          // rows on the strip seam: every alias (rare)
 #pragma unroll
-                                for (int k = 0; k < CPL; ++k)
-                                    if (x + k < a.nx) {
-                                        if (edge) {
+                                    for (int k = 0; k < CPL; ++k)
+                                        if (x + k < a.nx) {
                                             fast_store_edge(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, KOB_CX(np_, k));
                                             fast_store_edge(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, KOB_CX(nt_, k));
-                                        } else {
+                                        }
+                                } else {                                 // interior rows: own cell + ghost-column copy
+#pragma unroll
+                                    for (int k = 0; k < CPL; ++k)
+                                        if (x + k < a.nx) {
                                             pphi[k] = KOB_CX(np_, k);
                                             ptt[k] = KOB_CX(nt_, k);
+                                            if (x + k < GXR) { pphi[k + a.nx] = KOB_CX(np_, k); ptt[k + a.nx] = KOB_CX(nt_, k); }
+                                            if (x + k >= a.nx - GXR) { pphi[k - a.nx] = KOB_CX(np_, k); ptt[k - a.nx] = KOB_CX(nt_, k); }
                                         }
-                                    }
+                                }
+                            }
+                        }
+                    }
+                    // ---- GEN: prefetch theta of row r+1 (pass-1 row of the iteration after next) ----
+                    if (GEN) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) { thp0[k] = thp1[k]; thp1[k] = 0.f; }
+                        if (live) {
+                            const unsigned int yr1 = yrel + 3u;                              // (r + 1) - y0
+                            const int frow = ((y0 + (int)yr1 + GY) >> 5) - fby0;             // FBY == 32
+                            const bool lrow = (livemask >> min(max(frow, 0), 31)) & 1u;
+                            if (lrow && yr1 + 1u <= nvalid + 1u) {                           // rows y0-1 .. y1
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k)
+                                    if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(&a.self.theta[o2 + 3 * pitch + k]);
                             }
                         }
                     }
