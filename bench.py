@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=1024, help="edge of the CPU-baseline sample grid")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--field", default="seeded", choices=["seeded", "dense"],
+                    help="seeded: the BASELINE workload (Philox-placed nuclei); dense: every cell on a diffuse interface "
+                         "(worst case for the data-dependent path, reported as roofline.dense_field)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the secondary dense-field measurement")
     ap.add_argument("--strong", type=int, default=0,
                     help="strong scaling: a fixed STRONG x STRONG torus (BASELINE configs[3]: 65536) cut into row strips")
     return ap.parse_args()
@@ -164,6 +168,10 @@ def run_reference_arm(a, rank):
     print(json.dumps(line), flush=True)
 
 
+def sim_y0(ring):
+    return getattr(ring, "y0", 0)
+
+
 def workload_config(a, world):
     if a.strong:
         return {"workload": f"{a.strong}x{a.strong} torus strong-scaled over {world} GPU(s) ({a.strong}x{a.strong // world} cells per GPU), "
@@ -178,6 +186,23 @@ def workload_config(a, world):
             "nx": a.n, "ny_per_gpu": a.n, "substeps_per_step": a.substeps, "kernel": a.kernel, "precision": a.precision,
             "parallelism": f"row strips x{world}, in-kernel NVLink peer stores for the 2-row halo" if world > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (4 GiB of phi/T ping-pong per GPU vs 126 MB L2); no flush needed"}
+
+
+def dense_state(nx, ny, y0):
+    """A developed-field stand-in: every cell sits on a diffuse interface (0.05 <= phi <= 0.95, non-flat gradient
+    almost everywhere, T in [-0.3, 0.3]), so the data-dependent part of the step (angle re-assignment, anisotropy,
+    m(T), noise draw) runs for every cell — the worst case, where the seeded BASELINE workload is the best case."""
+    import numpy as np
+    x = np.arange(nx, dtype=np.float64)
+    y = np.arange(y0, y0 + ny, dtype=np.float64)
+    sx, cy = np.sin(2 * np.pi * x / 97.0).astype(np.float32), np.cos(2 * np.pi * y / 61.0).astype(np.float32)
+    cx, sy = np.cos(2 * np.pi * x / 53.0).astype(np.float32), np.sin(2 * np.pi * y / 131.0).astype(np.float32)
+    phi = np.multiply.outer(cy, sx)
+    phi *= np.float32(0.45)
+    phi += np.float32(0.5)
+    t = np.multiply.outer(sy, cx)
+    t *= np.float32(0.3)
+    return phi, t
 
 
 # ------------------------------------------------------------------------------------------ native arm
@@ -214,6 +239,9 @@ def main():
                      seed=SEED, noise_a=a.noise)
     sim = ring.strip
     ring.seed_nuclei(nuclei_positions(a.nuclei * (16 if a.strong else world), nx, nyg, SEED))
+    if a.field == "dense":
+        sim.set_fields(*dense_state(nx, ring.ny, sim_y0(ring)), None)
+        ring.refresh()
     cells_per_step = nx * ring.ny * a.substeps            # this rank
     total_cells_per_step = nx * nyg * a.substeps
 
@@ -249,6 +277,24 @@ def main():
         roof["traffic"] = json.load(open(tr)).get(f"{a.kernel}_{a.precision}_{a.n}")
     except Exception:
         pass
+
+    # ---- secondary: the same kernel on a dense (developed) field, N = 1 only ----
+    if world == 1 and a.kernel == "fast" and a.field == "seeded" and not a.no_dense and not a.strong:
+        saved = sim.fields()
+        ctr = sim.step_counter
+        sim.set_fields(*dense_state(nx, ring.ny, 0), np.zeros((ring.ny, nx), np.float32))
+        del_ms = None
+        sim.step(3 * a.substeps)
+        sim.sync()
+        d_steps = 5
+        del_ms = sim.step_timed(d_steps * a.substeps) / (d_steps * a.substeps)
+        roof["dense_field"] = {"value": nx * ring.ny / (del_ms * 1e-3) / 1e9, "unit": "Gcell/s", "launch_ms": del_ms,
+                               "frac": nx * ring.ny * 4 * elem / (del_ms * 1e-3) / 1e9 / peak,
+                               "what": "same grid, every cell on a diffuse interface (angle re-assignment, anisotropy, m(T) and the "
+                                       "noise draw run for every cell); 50 launches after 30 warm-up launches"}
+        sim.set_fields(*saved)
+        sim.step_counter = ctr
+        del saved
 
     # ---- end to end through the host-buffer plugin call ----
     e2e = None

@@ -89,7 +89,8 @@ struct kob_ctx {
     FastMaps maps{};
     int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
     double fast_frac_a = 0.9;
-    int fast_cta_jobs = 0;
+    int fast_cta_jobs = 1;        // CTA-wide jobs: 8 adjacent strips advance in lock-step (1920 B contiguous per row)
+    int fast_no_skip = 0;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
@@ -219,6 +220,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
     f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
     f.cta_jobs = c->fast_cta_jobs;
+    f.no_skip = c->fast_no_skip;
     f.nstrips_p = (f.nstrips + FAST_WARPS - 1) / FAST_WARPS * FAST_WARPS;
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
@@ -245,6 +247,7 @@ int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
     f.il_dt = P.inv_lapden * P.dt;
     f.two_pi = 2.0f * REF_PI_F;
     f.half_pi = 0.5f * REF_PI_F;
+    f.m_off = P.alpha_over_pi * 1.57079632679489662f;
     const bool rot = P.theta0 != 0.0f;
     const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
 #define KOB_FAST_CASE(NP_, JM_, ROT_)                                                          \
@@ -418,6 +421,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));
         int rcm = build_fast_maps(c);

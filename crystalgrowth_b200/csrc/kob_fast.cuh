@@ -44,12 +44,14 @@ struct FastArgs {
     int nstrips, nseg, yj, nseg_a, yj_b;
     int cta_jobs;                  // 1: a CTA claims 8 adjacent strips of one segment and keeps its warps in lock-step
     int nstrips_p;                 // strips padded to a multiple of the warps per CTA (cta_jobs only)
+    int no_skip;                   // test knob: never take the far-field (phi == +0) chunk shortcut
     // constants of the far field / held-with-theta==0 cells: eps and eps' at theta = 0
     float eps0, epsd0;
     float cj0, sj0;                // cos(j*theta0), sin(j*theta0) for the theta0 rotation
     float ebd;                     // epsbar*delta
     float il_dt;                   // inv_lapden*dt
     float two_pi, half_pi;         // 2*PI_F, 0.5*PI_F
+    float m_off;                   // (alpha/PI_F) * pi/2: m(T) for |gamma (T_eq - T)| -> inf
 };
 
 template <int NP>
@@ -67,6 +69,7 @@ struct FastGeom {
 #define KOB_FAST_NST 4
 #endif
 constexpr int FAST_RB = KOB_FAST_RB;     // rows per TMA chunk (= unroll of the row loop)
+static_assert(FAST_RB >= 4, "the far-field shortcut needs a chunk to cover the 4-row history of the register windows");
 constexpr int FAST_NST = KOB_FAST_NST;   // TMA stages per warp
 
 // one stage = phi box + T box, each padded to a multiple of 128 bytes (TMA shared-memory destination alignment)
@@ -140,6 +143,46 @@ __device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
     return r;
 }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// atan on [0, 1] for a pair of cells: w + w*t*Q(t), t = w^2, Q = degree-7 minimax (max abs error 8.5e-8 in FP32,
+// 1.4 ulp at pi/4 — the class of CUDA's atanf, at half the issue slots because both cells share every FFMA2).
+__device__ __forceinline__ float2 atan01_2(float2 w) {
+    const float2 t = f2mul(w, w);
+    float2 p = f2fma(f2(0.002622196450829506f), t, f2(-0.015132336877286434f));
+    p = f2fma(p, t, f2(0.04112152010202408f));
+    p = f2fma(p, t, f2(-0.0736667588353157f));
+    p = f2fma(p, t, f2(0.10573916882276535f));
+    p = f2fma(p, t, f2(-0.14185971021652222f));
+    p = f2fma(p, t, f2(0.1999039649963379f));
+    p = f2fma(p, t, f2(-0.33332985639572144f));
+    return f2fma(f2mul(w, t), p, w);
+}
+constexpr float HALF_PI_TRUE = 1.57079632679489662f;   // atan(+inf): range reduction of the atan itself (not PI_F)
+
+// (c + i s)^J for a pair of cells, J a compile-time constant
+template <int J>
+__device__ __forceinline__ void cpow2(float2 c, float2 s, float2& C, float2& S) {
+    if (J == 0) { C = f2(1.0f); S = f2(0.0f); return; }
+    if (J == 1) { C = c; S = s; return; }
+    float2 hc, hs;
+    cpow2<J / 2>(c, s, hc, hs);
+    const float2 qc = f2fma(hc, hc, f2neg(f2mul(hs, hs))), qs = f2mul(f2add(hc, hc), hs);
+    if (J & 1) { C = f2fma(qc, c, f2neg(f2mul(qs, s))); S = f2fma(qc, s, f2mul(qs, c)); }
+    else { C = qc; S = qs; }
+}
+__device__ __forceinline__ void cpow2_rt(int j, float2 c, float2 s, float2& C, float2& S) {   // 0 <= j <= 16, warp-uniform
+    float2 rc = f2(1.0f), rs = f2(0.0f);
+#pragma unroll
+    for (int bit = 4; bit >= 0; --bit) {
+        const float2 qc = f2fma(rc, rc, f2neg(f2mul(rs, rs))), qs = f2mul(f2add(rc, rc), rs);
+        rc = qc; rs = qs;
+        if ((j >> bit) & 1) { const float2 tc = f2fma(rc, c, f2neg(f2mul(rs, s))), ts = f2fma(rc, s, f2mul(rs, c)); rc = tc; rs = ts; }
+    }
+    C = rc; S = rs;
+}
 // component k (compile-time) of an array of cell pairs
 #define KOB_CX(arr, k) (((k) & 1) ? (arr)[(k) >> 1].y : (arr)[(k) >> 1].x)
 
@@ -157,14 +200,6 @@ __device__ __noinline__ void fast_mark_flags(uint32_t* self_f, uint32_t* lower_f
     a.self.tflags = self_f; a.lower.tflags = lower_f; a.upper.tflags = upper_f;
     a.lower.ny = ny_lower; a.upper.ny = ny_upper; a.nx = nx; a.ny = ny; a.nfbx = nfbx; a.nfby = nfby;
     mark_tile_flags<float>(a, x0, y0, tx, ty);
-}
-
-// Reference angle of a re-assigned cell (src/Kobayashi.cpp:154-167); gy/gx by reciprocal (2 ulp) — theta only
-// feeds cos/sin(j*theta) of later HELD steps, a rounding-level difference.
-__device__ __forceinline__ float fast_theta_value(float gx, float gy, bool flat, float pi, float two_pi, float half_pi) {
-    const float at = atanf(__fdividef(gy, gx));
-    const float th = gx > 0.f ? (gy < 0.f ? two_pi + at : at) : pi + at;
-    return flat ? (gy < 0.f ? -half_pi : half_pi) : th;
 }
 
 // JM: 4 / 6 = compile-time integer mode, 0 = run-time integer mode (prm.jmode in 0..16), -1 = any real j (trig).
@@ -273,8 +308,11 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 
         // The row loop, instantiated twice: GEN = false is the lean steady-state path (interior strip, no theta
         // to read, no seams); GEN = true additionally reads held theta, handles the ragged edge and the aliases.
-        auto body = [&](auto gen_tag) {
-            constexpr bool GEN = decltype(gen_tag)::value;
+        // MODE 0 (lean): interior strip, theta all zero in the footprint.  MODE 1 (live): interior strip, held
+        // theta is read.  MODE 2 (seam): additionally the ragged right edge and the alias stores.
+        auto body = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            constexpr bool GEN = MODE != 0, SEAM = MODE == 2;
             // register windows, one float2 per pair of adjacent cells; "r" is the phi row streamed in this iteration
             float2 po0[NP], po1[NP];               // phi rows r-2, r-1
             float2 gx1[NP], gx2[NP], gy2[NP];      // gx(r-1); gx, gy (r-2)
@@ -301,6 +339,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             const unsigned int nstore = mid_lane ? nvalid : 0u;    // rows this lane stores
             const float2 idx2 = f2(P.inv_dx), idy2 = f2(P.inv_dy), il2 = f2(P.inv_lapden), ildt2 = f2(f.il_dt);
             const float2 dtt2 = f2(P.dt_over_tau), K2 = f2(P.K), two2 = f2(2.0f), m12 = f2(-12.0f), B02 = f2(B0);
+            bool prevz = false;                    // !GEN: the previous chunk's phi rows were all +0
 
             for (int c = 0; c < nch; ++c) {
                 const unsigned int gi = gchunk + (unsigned int)c;
@@ -310,6 +349,62 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                 const float* sp = stages + st * STAGE_FLOATS + CPL * lane + CPL;   // this lane's own phi cells
                 const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
                 const int yrel0 = c * RB - 4;                                       // (r - 2) - y0 for rr = 0
+                if (!GEN) {
+                    // ---- far field: phi == +0 on all 64 own columns of this chunk's RB rows AND of the previous RB
+                    // rows.  Every phi term of the step is then exactly +0 and the register windows already sit at
+                    // their all-zero-input fixed point (each is a function of the last <= 5 streamed rows only), so
+                    // the chunk reduces to the T diffusion; outputs are bit-identical to the full path. ----
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) bits |= __float_as_uint(sp[rr * BW + k]);
+                    }
+                    const bool curz = !__any_sync(0xffffffffu, bits != 0u);
+                    const bool skip = curz && prevz && !f.no_skip;
+                    prevz = curz;
+                    if (skip) {
+#pragma unroll
+                        for (int rr = 0; rr < RB; ++rr) {
+                            const unsigned int yrel = (unsigned int)(yrel0 + rr);
+                            const float* row = stt + rr * BW;
+                            const float w = row[-1], ee = row[CPL];
+                            float2 tn[NP], thsum[NP];
+                            if (NP == 1) tn[0] = *reinterpret_cast<const float2*>(row);
+                            else { const float4 v = *reinterpret_cast<const float4*>(row); tn[0] = make_float2(v.x, v.y); tn[NP - 1] = make_float2(v.z, v.w); }
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                const float l = k == 0 ? w : KOB_CX(tn, k - 1), rgt = k == CPL - 1 ? ee : KOB_CX(tn, k + 1);
+                                KOB_CX(thsum, k) = l + rgt;
+                            }
+                            float2 nt_[NP];
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                const float2 tu_new = f2fma(two2, tn[p], thsum[p]);
+                                const float2 lapt = f2add(tlp1[p], tu_new);
+                                nt_[p] = f2fma(K2, f2(0.f), f2fma(lapt, ildt2, tq1[p]));       // :215 with phi+ - phi = +0
+                                tlp1[p] = f2fma(two2, thsum[p], f2fma(m12, tn[p], tu1[p]));
+                                tu1[p] = tu_new;
+                                tq1[p] = tn[p];
+                            }
+                            if (yrel < nstore) {
+                                if (NP == 1) {
+                                    *reinterpret_cast<float2*>(pphi) = f2(0.f);
+                                    *reinterpret_cast<float2*>(ptt) = nt_[0];
+                                } else {
+                                    *reinterpret_cast<float4*>(pphi) = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    *reinterpret_cast<float4*>(ptt) = make_float4(nt_[0].x, nt_[0].y, nt_[NP - 1].x, nt_[NP - 1].y);
+                                }
+                            }
+                            o2 += pitch;
+                            pphi += pitch;
+                            ptt += pitch;
+                        }
+                        __syncwarp();
+                        if (lane == 0 && c + NST < nch) issue(c + NST);
+                        continue;
+                    }
+                }
 #pragma unroll
                 for (int rr = 0; rr < RB; ++rr) {
                     const unsigned int yrel = (unsigned int)(yrel0 + rr);           // row of pass 2, relative to y0
@@ -376,52 +471,102 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                         if (busy) {
                             const int y = y0 + (int)yrel + 1;
                             const bool row_owned = yrel + 1u < nvalid;
+                            float2 Cc[NP], Ss[NP], th2[NP];
+                            bool flat[CPL], rare = false;
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                const float2 gx = gx1[p], gy = gyn[p];
+                                const float2 agx = make_float2(fabsf(gx.x), fabsf(gx.y)), agy = make_float2(fabsf(gy.x), fabsf(gy.y));
+                                // reference angle (:154-167): atan(|gy|/|gx|) folded into [0, pi/4], then the quadrant
+                                const float2 mn = make_float2(fminf(agx.x, agy.x), fminf(agx.y, agy.y));
+                                const float2 mx = make_float2(fmaxf(agx.x, agy.x), fmaxf(agx.y, agy.y));
+                                float2 r = atan01_2(f2mul(mn, make_float2(rcp_approx(mx.x), rcp_approx(mx.y))));
+                                const bool sw0 = agy.x > agx.x, sw1 = agy.y > agx.y;
+                                r = f2fma(r, make_float2(sw0 ? -1.0f : 1.0f, sw1 ? -1.0f : 1.0f),
+                                          make_float2(sw0 ? HALF_PI_TRUE : 0.0f, sw1 ? HALF_PI_TRUE : 0.0f));
+                                r.x = __uint_as_float(__float_as_uint(r.x) ^ ((__float_as_uint(gx.x) ^ __float_as_uint(gy.x)) & 0x80000000u));
+                                r.y = __uint_as_float(__float_as_uint(r.y) ^ ((__float_as_uint(gx.y) ^ __float_as_uint(gy.y)) & 0x80000000u));
+                                th2[p] = f2add(make_float2(gx.x < 0.f ? pi : (gy.x < 0.f ? f.two_pi : 0.0f),
+                                                           gx.y < 0.f ? pi : (gy.y < 0.f ? f.two_pi : 0.0f)), r);
+                                Cc[p] = f2(1.0f); Ss[p] = f2(0.0f);
+                                if (JM >= 0) {
+                                    const float2 r2 = f2fma(gx, gx, f2mul(gy, gy));
+                                    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                                    const float2 c1 = f2mul(gx, rinv), s1 = f2mul(gy, rinv);
+                                    if (JM == 0) cpow2_rt(P.jmode, c1, s1, Cc[p], Ss[p]); else cpow2<JM>(c1, s1, Cc[p], Ss[p]);
+                                    if (ROT) {
+                                        const float2 c2 = f2fma(Cc[p], f2(f.cj0), f2mul(Ss[p], f2(f.sj0)));
+                                        const float2 s2 = f2fma(Ss[p], f2(f.cj0), f2neg(f2mul(Cc[p], f2(f.sj0))));
+                                        Cc[p] = c2; Ss[p] = s2;
+                                    }
+                                }
+                            }
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
-                                const float gx = KOB_CX(gx1, k), gy = KOB_CX(gyn, k);
-                                const bool flat = (gx <= e) && (gx >= -e);                   // case A (:154-158)
-                                float C = 1.0f, S = 0.0f;
-                                if (JM >= 0) {
-                                    const float rinv = rsqrtf(fmaf(gx, gx, gy * gy));
-                                    const float c1 = flat ? 0.0f : gx * rinv;
-                                    const float s1 = flat ? (gy < 0.f ? -1.0f : 1.0f) : gy * rinv;
-                                    if (JM == 0) cpow_rt(P.jmode, c1, s1, C, S); else cpow<JM>(c1, s1, C, S);
-                                    if (ROT) { const float c2 = fmaf(C, f.cj0, S * f.sj0), s2 = fmaf(S, f.cj0, -C * f.sj0); C = c2; S = s2; }
-                                }
-                                const bool owned = asg[k] && row_owned && mid_lane && (!GEN || x + k < a.nx);
-                                if (JM < 0) {
-                                    if (asg[k]) {
-                                        const float th = fast_theta_value(gx, gy, flat, pi, f.two_pi, f.half_pi);
-                                        fast_sincos(P.aniso * (th - P.theta0), &S, &C);
-                                    }
-                                }
-                                if (owned) {
-                                    const float th = fast_theta_value(gx, gy, flat, pi, f.two_pi, f.half_pi);
-                                    if (GEN && (y < GY || y >= a.ny - GY))
-                                        fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
-                                    else {
-                                        float* pth = a.self.theta + (o2 + pitch + k);
-                                        *pth = th;
-                                        if (GEN) {
-                                            if (x + k < GXR) pth[a.nx] = th;
-                                            if (x + k >= a.nx - GXR) pth[-a.nx] = th;
+                                flat[k] = fabsf(KOB_CX(gx1, k)) <= e;                          // case A (:154-158)
+                                rare |= (asg[k] && flat[k]) || (GEN && th_old[k] != 0.f);
+                            }
+                            // rare cells: dead-band in gx (theta = +-PI_F/2) and held non-zero angles
+                            if (__any_sync(0xffffffffu, rare)) {
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k) {
+                                    if (asg[k] && flat[k]) {
+                                        const float sg = KOB_CX(gyn, k) < 0.f ? -1.0f : 1.0f;
+                                        KOB_CX(th2, k) = sg * f.half_pi;
+                                        if (JM >= 0) {
+                                            float C, S;
+                                            if (JM == 0) cpow_rt(P.jmode, 0.0f, sg, C, S); else cpow<(JM > 0 ? JM : 1)>(0.0f, sg, C, S);
+                                            if (ROT) { const float c2 = fmaf(C, f.cj0, S * f.sj0), s2 = fmaf(S, f.cj0, -C * f.sj0); C = c2; S = s2; }
+                                            KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
                                         }
-                                    }
-                                    assigned_any = true;
-                                }
-                                float ep = fmaf(f.ebd, C, P.epsbar);                         // :170
-                                float ed = P.neg_ebjd * S;                                   // :171
-                                if (GEN) {
-                                    if (!asg[k] && th_old[k] != 0.f) {                       // held, non-zero angle (rare)
+                                    } else if (GEN && th_old[k] != 0.f) {                      // held, non-zero angle
+                                        float C, S;
                                         fast_sincos(P.aniso * (th_old[k] - P.theta0), &S, &C);
-                                        ep = fmaf(f.ebd, C, P.epsbar);
-                                        ed = P.neg_ebjd * S;
-                                    } else if (!asg[k]) { ep = f.eps0; ed = f.epsd0; }
-                                } else if (!asg[k]) { ep = f.eps0; ed = f.epsd0; }
-                                KOB_CX(An, k) = ep * ep;
-                                const float B = ep * ed;
-                                KOB_CX(Pn, k) = B * gx;
-                                KOB_CX(Qn, k) = B * gy;
+                                        KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
+                                    }
+                                }
+                            }
+                            if (JM < 0) {                                                       // any real j: trig on the new angle
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k)
+                                    if (asg[k]) {
+                                        float C, S;
+                                        fast_sincos(P.aniso * (KOB_CX(th2, k) - P.theta0), &S, &C);
+                                        KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
+                                    }
+                            }
+                            // store the re-assigned angles of owned cells
+                            if (row_owned && mid_lane) {
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k) {
+                                    if (asg[k] && (!SEAM || x + k < a.nx)) {
+                                        const float th = KOB_CX(th2, k);
+                                        if (SEAM && (y < GY || y >= a.ny - GY))
+                                            fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
+                                        else {
+                                            float* pth = a.self.theta + (o2 + pitch + k);
+                                            *pth = th;
+                                            if (SEAM) {
+                                                if (x + k < GXR) pth[a.nx] = th;
+                                                if (x + k >= a.nx - GXR) pth[-a.nx] = th;
+                                            }
+                                        }
+                                        assigned_any = true;
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                float2 ep = f2fma(f2(f.ebd), Cc[p], f2(P.epsbar));              // :170
+                                float2 ed = f2mul(f2(P.neg_ebjd), Ss[p]);                        // :171
+                                const bool d0 = !asg[2 * p] && !(GEN && th_old[2 * p] != 0.f);   // holds theta = 0
+                                const bool d1 = !asg[2 * p + 1] && !(GEN && th_old[2 * p + 1] != 0.f);
+                                ep = make_float2(d0 ? f.eps0 : ep.x, d1 ? f.eps0 : ep.y);
+                                ed = make_float2(d0 ? f.epsd0 : ed.x, d1 ? f.epsd0 : ed.y);
+                                An[p] = f2mul(ep, ep);
+                                const float2 B = f2mul(ep, ed);
+                                Pn[p] = f2mul(B, gx1[p]);
+                                Qn[p] = f2mul(B, gyn[p]);
                             }
                         }
                         if (__any_sync(0xffffffffu, any_q)) {
@@ -448,11 +593,20 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                 }
                             }
 #pragma unroll
-                            for (int k = 0; k < CPL; ++k) {
-                                const float m = P.alpha_over_pi * atanf(P.gamma * (P.teq - KOB_CX(tq1, k)));    // :206
-                                float rv = KOB_CX(q, k) * ((KOB_CX(po0, k) - 0.5f) + m);                         // :214
-                                if (NOISE) rv = fmaf(P.noise_a * KOB_CX(q, k), rq[k] - 0.5f, rv);
-                                KOB_CX(radd, k) = rv;
+                            for (int p = 0; p < NP; ++p) {
+                                // m = (alpha/PI_F) atan(gamma (T_eq - T)), :206 — atan folded into [0, 1] by 1/|x|
+                                const float2 xa = f2mul(f2(P.gamma), f2sub(f2(P.teq), tq1[p]));
+                                const float ax0 = fabsf(xa.x), ax1 = fabsf(xa.y);
+                                const bool b0 = ax0 > 1.0f, b1 = ax1 > 1.0f;
+                                const float2 r = atan01_2(make_float2(b0 ? rcp_approx(ax0) : ax0, b1 ? rcp_approx(ax1) : ax1));
+                                float2 m = f2fma(r, make_float2(b0 ? -P.alpha_over_pi : P.alpha_over_pi, b1 ? -P.alpha_over_pi : P.alpha_over_pi),
+                                                 make_float2(b0 ? f.m_off : 0.0f, b1 ? f.m_off : 0.0f));
+                                m.x = __uint_as_float(__float_as_uint(m.x) ^ (__float_as_uint(xa.x) & 0x80000000u));
+                                m.y = __uint_as_float(__float_as_uint(m.y) ^ (__float_as_uint(xa.y) & 0x80000000u));
+                                float2 rv = f2mul(q[p], f2add(f2sub(po0[p], f2(0.5f)), m));                      // :214
+                                if (NOISE)
+                                    rv = f2fma(f2mul(f2(P.noise_a), q[p]), f2sub(make_float2(rq[2 * p], rq[2 * p + 1]), f2(0.5f)), rv);
+                                radd[p] = rv;
                             }
                         }
                     }
@@ -486,7 +640,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                             nt_[p] = f2fma(K2, f2sub(np_[p], po0[p]), f2fma(lapt, ildt2, tq1[p]));   // :215
                         }
                         if (yrel < nstore) {
-                            if (!GEN) {
+                            if (!SEAM) {
                                 if (NP == 1) {
                                     *reinterpret_cast<float2*>(pphi) = np_[0];
                                     *reinterpret_cast<float2*>(ptt) = nt_[0];
@@ -525,9 +679,17 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                             const int frow = ((y0 + (int)yr1 + GY) >> 5) - fby0;             // FBY == 32
                             const bool lrow = (livemask >> min(max(frow, 0), 31)) & 1u;
                             if (lrow && yr1 + 1u <= nvalid + 1u) {                           // rows y0-1 .. y1
+                                if (SEAM) {
 #pragma unroll
-                                for (int k = 0; k < CPL; ++k)
-                                    if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(&a.self.theta[o2 + 3 * pitch + k]);
+                                    for (int k = 0; k < CPL; ++k)
+                                        if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(&a.self.theta[o2 + 3 * pitch + k]);
+                                } else if (NP == 1) {
+                                    const float2 v = __ldg(reinterpret_cast<const float2*>(&a.self.theta[o2 + 3 * pitch]));
+                                    thp1[0] = v.x; thp1[1] = v.y;
+                                } else {
+                                    const float4 v = __ldg(reinterpret_cast<const float4*>(&a.self.theta[o2 + 3 * pitch]));
+                                    thp1[0] = v.x; thp1[1] = v.y; thp1[CPL - 2] = v.z; thp1[CPL - 1] = v.w;
+                                }
                             }
                         }
                     }
@@ -555,7 +717,9 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                 if (lane == 0 && c + NST < nch) issue(c + NST);
             }
         };
-        if (live || seam) body(std::true_type{}); else body(std::false_type{});
+        if (seam) body(std::integral_constant<int, 2>{});
+        else if (live) body(std::integral_constant<int, 1>{});
+        else body(std::integral_constant<int, 0>{});
 
         gchunk += (unsigned int)nch;
         if (__any_sync(0xffffffffu, assigned_any) && lane == 0) fast_mark_flags(a.self.tflags, a.lower.tflags, a.upper.tflags, a.lower.ny, a.upper.ny, a.nx, a.ny, a.nfbx, a.nfby,

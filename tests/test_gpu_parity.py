@@ -359,13 +359,40 @@ def test_linked_strips_on_one_gpu_equal_single_domain(po, cg, kernel, prec, nstr
 
 
 # ---------------------------------------------------------------------------------------------- FAST variants
+@pytest.mark.parametrize("cta", [0, 1])
+@pytest.mark.parametrize("np_", [1, 2])
+def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, np_):
+    """Chunks whose phi rows (and the 4 rows before them) are all +0 skip the phi arithmetic and only diffuse T.
+    That must not change a single bit: run with the shortcut disabled (KOB_FAST_NOSKIP=1) and compare.  The grid
+    is wide/tall enough for whole far-field jobs, partial ones next to the crystals, and heat (T != 0) diffusing
+    into phi == 0 territory; noise is on."""
+    def run(noskip):
+        monkeypatch.setenv("KOB_FAST_NOSKIP", str(noskip))
+        monkeypatch.setenv("KOB_FAST_CTA", str(cta))
+        monkeypatch.setenv("KOB_FAST_NP", str(np_))
+        monkeypatch.setenv("KOB_FAST_YJ", "32")
+        g = cg.Kobayashi(700, 300, 1e-4, kernel="fast", seed=11, noise_a=0.01)
+        g.clear()
+        for (x, y) in [(0, 0), (350, 150), (699, 299), (100, 40), (520, 222)]:
+            g.add_nucleus(x, y)
+        g.step(150)
+        out = g.fields()
+        g.close()
+        return out
+    a, b = run(0), run(1)
+    assert (a[0] == 0).mean() > 0.5 and (a[1] != 0).mean() > (a[0] != 0).mean()      # the case is really exercised
+    assert all(bit_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("cta", [0, 1])
 @pytest.mark.parametrize("np_,yj", [(1, 8), (2, 256), (2, 12), (1, 5)])
-def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj):
+def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj, cta):
     """The FAST kernel's decomposition knobs (cells per lane, rows per job) do not change results: every variant
     passes the single-step gate, and the job height is bit-neutral."""
     def run(env_np, env_yj, nx=150, ny=90, steps=12):
         monkeypatch.setenv("KOB_FAST_NP", str(env_np))
         monkeypatch.setenv("KOB_FAST_YJ", str(env_yj))
+        monkeypatch.setenv("KOB_FAST_CTA", str(cta))
         g = cg.Kobayashi(nx, ny, 1e-4, kernel="fast", seed=9, noise_a=0.01)
         g.clear()
         for (x, y) in [(0, 0), (75, 45), (149, 89), (30, 7), (120, 8)]:
