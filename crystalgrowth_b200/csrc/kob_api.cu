@@ -248,6 +248,12 @@ int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
     f.two_pi = 2.0f * REF_PI_F;
     f.half_pi = 0.5f * REF_PI_F;
     f.m_off = P.alpha_over_pi * 1.57079632679489662f;
+    for (int r = 0; r < 10; ++r) {
+        f.pk[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
+        f.pk[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    f.pc2 = (uint32_t)a.step;
+    f.pc3 = (uint32_t)(a.step >> 32);
     const bool rot = P.theta0 != 0.0f;
     const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
 #define KOB_FAST_CASE(NP_, JM_, ROT_)                                                          \

@@ -52,7 +52,26 @@ struct FastArgs {
     float il_dt;                   // inv_lapden*dt
     float two_pi, half_pi;         // 2*PI_F, 0.5*PI_F
     float m_off;                   // (alpha/PI_F) * pi/2: m(T) for |gamma (T_eq - T)| -> inf
+    uint32_t pk[20];               // Philox round keys: pk[2r] = seed_lo + r*W0, pk[2r+1] = seed_hi + r*W1
+    uint32_t pc2, pc3;             // Philox counter words 2, 3 = (step_lo, step_hi)
 };
+
+// Philox4x32-10 with the per-round keys (key + r * Weyl) precomputed on the host into the constant bank and the
+// (step_lo, step_hi) half of the counter taken from there too.  Same bits as kob_math.h's philox4x32_10.
+__device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, uint32_t c1) {
+    uint32_t c2 = f.pc2, c3 = f.pc3;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ f.pk[2 * r];
+        c2 = h0 ^ c3 ^ f.pk[2 * r + 1];
+        c1 = l1; c3 = l0;
+    }
+    Philox4 o;
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
 
 template <int NP>
 struct FastGeom {
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < CPL; ++k) thp0[k] = thp1[k] = 0.f;
             // running pointers to cell (x, r-2) of the output arrays / theta
-            long long o2 = pidx<float>(pitch, x, y0 - 4);
+            const long long o2 = pidx<float>(pitch, x, y0 - 4);
             float* pphi = phi_out + o2;
             float* ptt = t_out + o2;
             const unsigned int nvalid = (unsigned int)(y1 - y0);
@@ -340,6 +359,10 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             const float2 idx2 = f2(P.inv_dx), idy2 = f2(P.inv_dy), il2 = f2(P.inv_lapden), ildt2 = f2(f.il_dt);
             const float2 dtt2 = f2(P.dt_over_tau), K2 = f2(P.K), two2 = f2(2.0f), m12 = f2(-12.0f), B02 = f2(B0);
             bool prevz = false;                    // !GEN: the previous chunk's phi rows were all +0
+            bool have_next = false;                // NP = 1 noise: the odd row's Philox words were drawn at the even row
+            uint32_t nxa = 0u, nxb = 0u;
+            float* pthe = a.self.theta + (o2 + pitch);   // theta of cell (x, r-1): the row pass 1 re-assigns
+            const long long pitch2 = 2 * pitch;
 
             for (int c = 0; c < nch; ++c) {
                 const unsigned int gi = gchunk + (unsigned int)c;
@@ -396,14 +419,19 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                                     *reinterpret_cast<float4*>(ptt) = make_float4(nt_[0].x, nt_[0].y, nt_[NP - 1].x, nt_[NP - 1].y);
                                 }
                             }
-                            o2 += pitch;
                             pphi += pitch;
                             ptt += pitch;
+                            pthe += pitch;
                         }
                         __syncwarp();
                         if (lane == 0 && c + NST < nch) issue(c + NST);
                         continue;
                     }
+                }
+                bool lrow_c = false;          // GEN: some theta-flag row under this chunk's prefetch rows (r+1) is live
+                if (GEN && live) {
+                    const int f0 = ((y0 + yrel0 + 3 + GY) >> 5) - fby0, f1 = ((y0 + yrel0 + RB + 2 + GY) >> 5) - fby0;   // FBY == 32
+                    lrow_c = ((livemask >> min(max(f0, 0), 31)) | (livemask >> min(max(f1, 0), 31))) & 1u;
                 }
 #pragma unroll
                 for (int rr = 0; rr < RB; ++rr) {
@@ -458,156 +486,162 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) interesting |= thp0[k] != 0.f;       // a held cell may carry an angle
                     }
-                    // ONE vote per row; everything data dependent lives in this cold block
+                    // ONE vote per row; everything data dependent lives in this cold block, as one straight-line
+                    // region (angle, anisotropy, m(T) and the noise draw interleave in the issue stream)
+                    if ((rr & 1) == 0) have_next = false;
                     if (__any_sync(0xffffffffu, interesting)) {
-                        bool any_asg = false, any_q = false;
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) { any_asg |= asg[k]; any_q |= KOB_CX(q, k) != 0.f; }
+                        const bool row_owned = yrel + 1u < nvalid;
                         float th_old[CPL];
-                        bool nz = false;
 #pragma unroll
-                        for (int k = 0; k < CPL; ++k) { th_old[k] = (GEN && !asg[k]) ? thp0[k] : 0.f; nz |= th_old[k] != 0.f; }
-                        const bool busy = __any_sync(0xffffffffu, any_asg || nz);
-                        if (busy) {
-                            const int y = y0 + (int)yrel + 1;
-                            const bool row_owned = yrel + 1u < nvalid;
-                            float2 Cc[NP], Ss[NP], th2[NP];
-                            bool flat[CPL], rare = false;
+                        for (int k = 0; k < CPL; ++k) th_old[k] = (GEN && !asg[k]) ? thp0[k] : 0.f;
+                        float2 c1[NP], s1[NP], th2[NP];
+                        bool rare = false;
 #pragma unroll
-                            for (int p = 0; p < NP; ++p) {
-                                const float2 gx = gx1[p], gy = gyn[p];
-                                const float2 agx = make_float2(fabsf(gx.x), fabsf(gx.y)), agy = make_float2(fabsf(gy.x), fabsf(gy.y));
-                                // reference angle (:154-167): atan(|gy|/|gx|) folded into [0, pi/4], then the quadrant
-                                const float2 mn = make_float2(fminf(agx.x, agy.x), fminf(agx.y, agy.y));
-                                const float2 mx = make_float2(fmaxf(agx.x, agy.x), fmaxf(agx.y, agy.y));
-                                float2 r = atan01_2(f2mul(mn, make_float2(rcp_approx(mx.x), rcp_approx(mx.y))));
-                                const bool sw0 = agy.x > agx.x, sw1 = agy.y > agx.y;
-                                r = f2fma(r, make_float2(sw0 ? -1.0f : 1.0f, sw1 ? -1.0f : 1.0f),
-                                          make_float2(sw0 ? HALF_PI_TRUE : 0.0f, sw1 ? HALF_PI_TRUE : 0.0f));
-                                r.x = __uint_as_float(__float_as_uint(r.x) ^ ((__float_as_uint(gx.x) ^ __float_as_uint(gy.x)) & 0x80000000u));
-                                r.y = __uint_as_float(__float_as_uint(r.y) ^ ((__float_as_uint(gx.y) ^ __float_as_uint(gy.y)) & 0x80000000u));
-                                th2[p] = f2add(make_float2(gx.x < 0.f ? pi : (gy.x < 0.f ? f.two_pi : 0.0f),
-                                                           gx.y < 0.f ? pi : (gy.y < 0.f ? f.two_pi : 0.0f)), r);
-                                Cc[p] = f2(1.0f); Ss[p] = f2(0.0f);
-                                if (JM >= 0) {
-                                    const float2 r2 = f2fma(gx, gx, f2mul(gy, gy));
-                                    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-                                    const float2 c1 = f2mul(gx, rinv), s1 = f2mul(gy, rinv);
-                                    if (JM == 0) cpow2_rt(P.jmode, c1, s1, Cc[p], Ss[p]); else cpow2<JM>(c1, s1, Cc[p], Ss[p]);
-                                    if (ROT) {
-                                        const float2 c2 = f2fma(Cc[p], f2(f.cj0), f2mul(Ss[p], f2(f.sj0)));
-                                        const float2 s2 = f2fma(Ss[p], f2(f.cj0), f2neg(f2mul(Cc[p], f2(f.sj0))));
-                                        Cc[p] = c2; Ss[p] = s2;
-                                    }
-                                }
-                            }
+                        for (int p = 0; p < NP; ++p) {
+                            const float2 gx = gx1[p], gy = gyn[p];
+                            const float2 agx = make_float2(fabsf(gx.x), fabsf(gx.y)), agy = make_float2(fabsf(gy.x), fabsf(gy.y));
+                            // reference angle (:154-167): atan(|gy|/|gx|) folded into [0, pi/4], then the quadrant
+                            const float2 mn = make_float2(fminf(agx.x, agy.x), fminf(agx.y, agy.y));
+                            const float2 mx = make_float2(fmaxf(agx.x, agy.x), fmaxf(agx.y, agy.y));
+                            float2 r = atan01_2(f2mul(mn, make_float2(rcp_approx(mx.x), rcp_approx(mx.y))));
+                            const bool sw0 = agy.x > agx.x, sw1 = agy.y > agx.y;
+                            r = f2fma(r, make_float2(sw0 ? -1.0f : 1.0f, sw1 ? -1.0f : 1.0f),
+                                      make_float2(sw0 ? HALF_PI_TRUE : 0.0f, sw1 ? HALF_PI_TRUE : 0.0f));
+                            r.x = __uint_as_float(__float_as_uint(r.x) ^ ((__float_as_uint(gx.x) ^ __float_as_uint(gy.x)) & 0x80000000u));
+                            r.y = __uint_as_float(__float_as_uint(r.y) ^ ((__float_as_uint(gx.y) ^ __float_as_uint(gy.y)) & 0x80000000u));
+                            th2[p] = f2add(make_float2(gx.x < 0.f ? pi : (gy.x < 0.f ? f.two_pi : 0.0f),
+                                                       gx.y < 0.f ? pi : (gy.y < 0.f ? f.two_pi : 0.0f)), r);
+                            // unit vector of the gradient (trig-free anisotropy)
+                            const float2 r2 = f2fma(gx, gx, f2mul(gy, gy));
+                            const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+                            c1[p] = f2mul(gx, rinv); s1[p] = f2mul(gy, rinv);
+                        }
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k)
+                            rare |= (asg[k] && fabsf(KOB_CX(gx1, k)) <= e) || (GEN && th_old[k] != 0.f);
+                        // rare cells: dead-band in gx (case A, :154-158: theta = +-PI_F/2) and held non-zero angles,
+                        // whose unit vector is (cos theta, sin theta) by MUFU after folding theta into [-pi, pi]
+                        if (__any_sync(0xffffffffu, rare)) {
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
-                                flat[k] = fabsf(KOB_CX(gx1, k)) <= e;                          // case A (:154-158)
-                                rare |= (asg[k] && flat[k]) || (GEN && th_old[k] != 0.f);
-                            }
-                            // rare cells: dead-band in gx (theta = +-PI_F/2) and held non-zero angles
-                            if (__any_sync(0xffffffffu, rare)) {
-#pragma unroll
-                                for (int k = 0; k < CPL; ++k) {
-                                    if (asg[k] && flat[k]) {
-                                        const float sg = KOB_CX(gyn, k) < 0.f ? -1.0f : 1.0f;
-                                        KOB_CX(th2, k) = sg * f.half_pi;
-                                        if (JM >= 0) {
-                                            float C, S;
-                                            if (JM == 0) cpow_rt(P.jmode, 0.0f, sg, C, S); else cpow<(JM > 0 ? JM : 1)>(0.0f, sg, C, S);
-                                            if (ROT) { const float c2 = fmaf(C, f.cj0, S * f.sj0), s2 = fmaf(S, f.cj0, -C * f.sj0); C = c2; S = s2; }
-                                            KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
-                                        }
-                                    } else if (GEN && th_old[k] != 0.f) {                      // held, non-zero angle
-                                        float C, S;
-                                        fast_sincos(P.aniso * (th_old[k] - P.theta0), &S, &C);
-                                        KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
-                                    }
+                                if (asg[k] && fabsf(KOB_CX(gx1, k)) <= e) {
+                                    const float sg = KOB_CX(gyn, k) < 0.f ? -1.0f : 1.0f;
+                                    KOB_CX(th2, k) = sg * f.half_pi;
+                                    KOB_CX(c1, k) = 0.0f; KOB_CX(s1, k) = sg;
+                                } else if (GEN && th_old[k] != 0.f) {
+                                    float t = th_old[k];
+                                    if (t > 3.14159265358979f) t = fmaf(-1.0f, 6.28318548202514648f, t) + 1.74845553e-7f;   // - 2 pi (hi, lo)
+                                    KOB_CX(c1, k) = __cosf(t); KOB_CX(s1, k) = __sinf(t);
                                 }
-                            }
-                            if (JM < 0) {                                                       // any real j: trig on the new angle
-#pragma unroll
-                                for (int k = 0; k < CPL; ++k)
-                                    if (asg[k]) {
-                                        float C, S;
-                                        fast_sincos(P.aniso * (KOB_CX(th2, k) - P.theta0), &S, &C);
-                                        KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
-                                    }
-                            }
-                            // store the re-assigned angles of owned cells
-                            if (row_owned && mid_lane) {
-#pragma unroll
-                                for (int k = 0; k < CPL; ++k) {
-                                    if (asg[k] && (!SEAM || x + k < a.nx)) {
-                                        const float th = KOB_CX(th2, k);
-                                        if (SEAM && (y < GY || y >= a.ny - GY))
-                                            fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
-                                        else {
-                                            float* pth = a.self.theta + (o2 + pitch + k);
-                                            *pth = th;
-                                            if (SEAM) {
-                                                if (x + k < GXR) pth[a.nx] = th;
-                                                if (x + k >= a.nx - GXR) pth[-a.nx] = th;
-                                            }
-                                        }
-                                        assigned_any = true;
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int p = 0; p < NP; ++p) {
-                                float2 ep = f2fma(f2(f.ebd), Cc[p], f2(P.epsbar));              // :170
-                                float2 ed = f2mul(f2(P.neg_ebjd), Ss[p]);                        // :171
-                                const bool d0 = !asg[2 * p] && !(GEN && th_old[2 * p] != 0.f);   // holds theta = 0
-                                const bool d1 = !asg[2 * p + 1] && !(GEN && th_old[2 * p + 1] != 0.f);
-                                ep = make_float2(d0 ? f.eps0 : ep.x, d1 ? f.eps0 : ep.y);
-                                ed = make_float2(d0 ? f.epsd0 : ed.x, d1 ? f.epsd0 : ed.y);
-                                An[p] = f2mul(ep, ep);
-                                const float2 B = f2mul(ep, ed);
-                                Pn[p] = f2mul(B, gx1[p]);
-                                Qn[p] = f2mul(B, gyn[p]);
                             }
                         }
-                        if (__any_sync(0xffffffffu, any_q)) {
-                            // reaction term q*((phi - 1/2) + m(T)) [+ noise] of row r-2, :206-214
-                            float rq[4];
-                            if (NOISE) {
-                                const int y = y0 + (int)yrel;
-                                if (a.noise_field) {
+                        float2 Cc[NP], Ss[NP];
 #pragma unroll
-                                    for (int k = 0; k < CPL; ++k)
-                                        rq[k] = (KOB_CX(q, k) != 0.f && x + k >= 0 && x + k < a.nx && yrel < nvalid)
-                                                    ? __ldg(&a.noise_field[(long long)(x + k) + (long long)a.nx * y]) : 0.5f;
-                                } else {
-                                    const Philox4 ph = philox4x32_10((uint32_t)x >> 2, (uint32_t)(a.y0 + y), (uint32_t)a.step,
-                                                                     (uint32_t)(a.step >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                                    if (NP == 2) {
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) rq[k] = noise_from_word(ph.w[k]);
-                                    } else {
-                                        const bool hi = (x & 2) != 0;
-                                        rq[0] = noise_from_word(hi ? ph.w[2] : ph.w[0]);
-                                        rq[1] = noise_from_word(hi ? ph.w[3] : ph.w[1]);
-                                    }
+                        for (int p = 0; p < NP; ++p) {
+                            Cc[p] = f2(1.0f); Ss[p] = f2(0.0f);
+                            if (JM >= 0) {
+                                if (JM == 0) cpow2_rt(P.jmode, c1[p], s1[p], Cc[p], Ss[p]); else cpow2<JM>(c1[p], s1[p], Cc[p], Ss[p]);
+                                if (ROT) {
+                                    const float2 c2 = f2fma(Cc[p], f2(f.cj0), f2mul(Ss[p], f2(f.sj0)));
+                                    const float2 s2 = f2fma(Ss[p], f2(f.cj0), f2neg(f2mul(Cc[p], f2(f.sj0))));
+                                    Cc[p] = c2; Ss[p] = s2;
                                 }
                             }
+                        }
+                        if (JM < 0) {                                                       // any real j: trig on the angle
 #pragma unroll
-                            for (int p = 0; p < NP; ++p) {
-                                // m = (alpha/PI_F) atan(gamma (T_eq - T)), :206 — atan folded into [0, 1] by 1/|x|
-                                const float2 xa = f2mul(f2(P.gamma), f2sub(f2(P.teq), tq1[p]));
-                                const float ax0 = fabsf(xa.x), ax1 = fabsf(xa.y);
-                                const bool b0 = ax0 > 1.0f, b1 = ax1 > 1.0f;
-                                const float2 r = atan01_2(make_float2(b0 ? rcp_approx(ax0) : ax0, b1 ? rcp_approx(ax1) : ax1));
-                                float2 m = f2fma(r, make_float2(b0 ? -P.alpha_over_pi : P.alpha_over_pi, b1 ? -P.alpha_over_pi : P.alpha_over_pi),
-                                                 make_float2(b0 ? f.m_off : 0.0f, b1 ? f.m_off : 0.0f));
-                                m.x = __uint_as_float(__float_as_uint(m.x) ^ (__float_as_uint(xa.x) & 0x80000000u));
-                                m.y = __uint_as_float(__float_as_uint(m.y) ^ (__float_as_uint(xa.y) & 0x80000000u));
-                                float2 rv = f2mul(q[p], f2add(f2sub(po0[p], f2(0.5f)), m));                      // :214
-                                if (NOISE)
-                                    rv = f2fma(f2mul(f2(P.noise_a), q[p]), f2sub(make_float2(rq[2 * p], rq[2 * p + 1]), f2(0.5f)), rv);
-                                radd[p] = rv;
+                            for (int k = 0; k < CPL; ++k) {
+                                const float th = asg[k] ? KOB_CX(th2, k) : th_old[k];
+                                if (asg[k] || th != 0.f) {
+                                    float C, S;
+                                    fast_sincos(P.aniso * (th - P.theta0), &S, &C);
+                                    KOB_CX(Cc, k) = C; KOB_CX(Ss, k) = S;
+                                }
                             }
+                        }
+                        // store the re-assigned angles of owned cells
+                        if (row_owned && mid_lane) {
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) {
+                                if (asg[k] && (!SEAM || x + k < a.nx)) {
+                                    const float th = KOB_CX(th2, k);
+                                    const int y = y0 + (int)yrel + 1;
+                                    if (SEAM && (y < GY || y >= a.ny - GY))
+                                        fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
+                                    else {
+                                        float* pth = pthe + k;
+                                        *pth = th;
+                                        if (SEAM) {
+                                            if (x + k < GXR) pth[a.nx] = th;
+                                            if (x + k >= a.nx - GXR) pth[-a.nx] = th;
+                                        }
+                                    }
+                                    assigned_any = true;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            float2 ep = f2fma(f2(f.ebd), Cc[p], f2(P.epsbar));              // :170
+                            float2 ed = f2mul(f2(P.neg_ebjd), Ss[p]);                        // :171
+                            const bool d0 = !asg[2 * p] && !(GEN && th_old[2 * p] != 0.f);   // holds theta = 0
+                            const bool d1 = !asg[2 * p + 1] && !(GEN && th_old[2 * p + 1] != 0.f);
+                            ep = make_float2(d0 ? f.eps0 : ep.x, d1 ? f.eps0 : ep.y);
+                            ed = make_float2(d0 ? f.epsd0 : ed.x, d1 ? f.epsd0 : ed.y);
+                            An[p] = f2mul(ep, ep);
+                            const float2 B = f2mul(ep, ed);
+                            Pn[p] = f2mul(B, gx1[p]);
+                            Qn[p] = f2mul(B, gyn[p]);
+                        }
+                        // ---- reaction term q*((phi - 1/2) + m(T)) [+ noise] of row r-2, :206-214 ----
+                        float2 rq[NP];                      // r - 1/2 of the noise draw
+                        if (NOISE) {
+                            const int y = y0 + (int)yrel;
+                            if (a.noise_field) {
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k)
+                                    KOB_CX(rq, k) = ((KOB_CX(q, k) != 0.f && x + k >= 0 && x + k < a.nx && yrel < nvalid)
+                                                ? __ldg(&a.noise_field[(long long)(x + k) + (long long)a.nx * y]) : 0.5f) - 0.5f;
+                            } else if (NP == 2) {
+                                const Philox4 ph = fast_philox(f, (uint32_t)x >> 2, (uint32_t)(a.y0 + y));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) KOB_CX(rq, k) = fmaf((float)(ph.w[k] >> 8), 5.9604644775390625e-8f, -0.5f);
+                            } else {
+                                // NP = 1: lanes (2m+1, 2m+2) share a Philox block (4 cells); over a row pair the low lane
+                                // draws the block of row y, the high lane the block of row y+1, and they swap halves
+                                const bool hi = (x & 2) != 0;
+                                uint32_t wa, wb;
+                                if ((rr & 1) == 0) {
+                                    const Philox4 ph = fast_philox(f, (uint32_t)x >> 2, (uint32_t)(a.y0 + y) + (hi ? 1u : 0u));
+                                    const int partner = hi ? lane - 1 : lane + 1;
+                                    const uint32_t ra = __shfl_sync(0xffffffffu, hi ? ph.w[0] : ph.w[2], partner);
+                                    const uint32_t rb = __shfl_sync(0xffffffffu, hi ? ph.w[1] : ph.w[3], partner);
+                                    wa = hi ? ra : ph.w[0]; wb = hi ? rb : ph.w[1];
+                                    nxa = hi ? ph.w[2] : ra; nxb = hi ? ph.w[3] : rb;
+                                    have_next = true;
+                                } else if (have_next) {
+                                    wa = nxa; wb = nxb;
+                                } else {
+                                    const Philox4 ph = fast_philox(f, (uint32_t)x >> 2, (uint32_t)(a.y0 + y));
+                                    wa = hi ? ph.w[2] : ph.w[0]; wb = hi ? ph.w[3] : ph.w[1];
+                                }
+                                rq[0] = f2fma(make_float2((float)(wa >> 8), (float)(wb >> 8)), f2(5.9604644775390625e-8f), f2(-0.5f));
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            // m = (alpha/PI_F) atan(gamma (T_eq - T)), :206 — atan folded into [0, 1] by 1/|x|
+                            const float2 xa = f2mul(f2(P.gamma), f2sub(f2(P.teq), tq1[p]));
+                            const float ax0 = fabsf(xa.x), ax1 = fabsf(xa.y);
+                            const bool b0 = ax0 > 1.0f, b1 = ax1 > 1.0f;
+                            const float2 r = atan01_2(make_float2(b0 ? rcp_approx(ax0) : ax0, b1 ? rcp_approx(ax1) : ax1));
+                            float2 m = f2fma(r, make_float2(b0 ? -P.alpha_over_pi : P.alpha_over_pi, b1 ? -P.alpha_over_pi : P.alpha_over_pi),
+                                             make_float2(b0 ? f.m_off : 0.0f, b1 ? f.m_off : 0.0f));
+                            m.x = __uint_as_float(__float_as_uint(m.x) ^ (__float_as_uint(xa.x) & 0x80000000u));
+                            m.y = __uint_as_float(__float_as_uint(m.y) ^ (__float_as_uint(xa.y) & 0x80000000u));
+                            float2 rv = f2mul(q[p], f2add(f2sub(po0[p], f2(0.5f)), m));                      // :214
+                            if (NOISE) rv = f2fma(f2mul(f2(P.noise_a), q[p]), rq[p], rv);
+                            radd[p] = rv;
                         }
                     }
                     // ---- pass 2 for row y = r-2 (computed unconditionally; stores predicated on the row being owned) ----
@@ -674,29 +708,25 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                     if (GEN) {
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) { thp0[k] = thp1[k]; thp1[k] = 0.f; }
-                        if (live) {
-                            const unsigned int yr1 = yrel + 3u;                              // (r + 1) - y0
-                            const int frow = ((y0 + (int)yr1 + GY) >> 5) - fby0;             // FBY == 32
-                            const bool lrow = (livemask >> min(max(frow, 0), 31)) & 1u;
-                            if (lrow && yr1 + 1u <= nvalid + 1u) {                           // rows y0-1 .. y1
-                                if (SEAM) {
+                        if (lrow_c && yrel + 4u <= nvalid + 1u) {                            // theta rows y0-1 .. y1
+                            const float* pf = pthe + pitch2;                                 // theta(x, r+1)
+                            if (SEAM) {
 #pragma unroll
-                                    for (int k = 0; k < CPL; ++k)
-                                        if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(&a.self.theta[o2 + 3 * pitch + k]);
-                                } else if (NP == 1) {
-                                    const float2 v = __ldg(reinterpret_cast<const float2*>(&a.self.theta[o2 + 3 * pitch]));
-                                    thp1[0] = v.x; thp1[1] = v.y;
-                                } else {
-                                    const float4 v = __ldg(reinterpret_cast<const float4*>(&a.self.theta[o2 + 3 * pitch]));
-                                    thp1[0] = v.x; thp1[1] = v.y; thp1[CPL - 2] = v.z; thp1[CPL - 1] = v.w;
-                                }
+                                for (int k = 0; k < CPL; ++k)
+                                    if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(pf + k);
+                            } else if (NP == 1) {
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(pf));
+                                thp1[0] = v.x; thp1[1] = v.y;
+                            } else {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(pf));
+                                thp1[0] = v.x; thp1[1] = v.y; thp1[CPL - 2] = v.z; thp1[CPL - 1] = v.w;
                             }
                         }
                     }
                     // ---- rotate the register windows ----
-                    o2 += pitch;
                     pphi += pitch;
                     ptt += pitch;
+                    pthe += pitch;
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
                         tlp1[p] = f2fma(two2, thsum[p], f2fma(m12, tn[p], tu1[p]));          // c_T(r-1) + u_T(r-2)
