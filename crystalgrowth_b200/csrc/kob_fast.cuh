@@ -62,11 +62,10 @@ __device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, u
     uint32_t c2 = f.pc2, c3 = f.pc3;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ f.pk[2 * r];
-        c2 = h0 ^ c3 ^ f.pk[2 * r + 1];
-        c1 = l1; c3 = l0;
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ f.pk[2 * r];
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ f.pk[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0;
     }
     Philox4 o;
     o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
@@ -436,6 +435,12 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 #pragma unroll
                 for (int rr = 0; rr < RB; ++rr) {
                     const unsigned int yrel = (unsigned int)(yrel0 + rr);           // row of pass 2, relative to y0
+                    // horizontal neighbours of the pass-1 products of row r-2, issued early: the shuffle latency hides
+                    // behind this row's pass 1
+                    const float A_w = __shfl_up_sync(0xffffffffu, A2[NP - 1].y, 1);
+                    const float A_e = __shfl_down_sync(0xffffffffu, A2[0].x, 1);
+                    const float Q_w = __shfl_up_sync(0xffffffffu, Q2[NP - 1].y, 1);
+                    const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0].x, 1);
                     // ---- phi row r: own cells, horizontal sums and x-gradient ----
                     float2 pn[NP], hsum[NP], gxn[NP];
                     {
@@ -524,15 +529,15 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                         if (__any_sync(0xffffffffu, rare)) {
 #pragma unroll
                             for (int k = 0; k < CPL; ++k) {
-                                if (asg[k] && fabsf(KOB_CX(gx1, k)) <= e) {
-                                    const float sg = KOB_CX(gyn, k) < 0.f ? -1.0f : 1.0f;
-                                    KOB_CX(th2, k) = sg * f.half_pi;
-                                    KOB_CX(c1, k) = 0.0f; KOB_CX(s1, k) = sg;
-                                } else if (GEN && th_old[k] != 0.f) {
-                                    float t = th_old[k];
-                                    if (t > 3.14159265358979f) t = fmaf(-1.0f, 6.28318548202514648f, t) + 1.74845553e-7f;   // - 2 pi (hi, lo)
-                                    KOB_CX(c1, k) = __cosf(t); KOB_CX(s1, k) = __sinf(t);
-                                }
+                                const bool fl = asg[k] && fabsf(KOB_CX(gx1, k)) <= e;
+                                const bool held = GEN && th_old[k] != 0.f;
+                                const float sg = KOB_CX(gyn, k) < 0.f ? -1.0f : 1.0f;
+                                float t = th_old[k];
+                                if (GEN) t = t > 3.14159265358979f ? fmaf(-1.0f, 6.28318548202514648f, t) + 1.74845553e-7f : t;   // - 2 pi (hi, lo)
+                                const float ct = GEN ? __cosf(t) : 0.f, st = GEN ? __sinf(t) : 0.f;
+                                KOB_CX(th2, k) = fl ? sg * f.half_pi : KOB_CX(th2, k);
+                                KOB_CX(c1, k) = fl ? 0.0f : (held ? ct : KOB_CX(c1, k));
+                                KOB_CX(s1, k) = fl ? sg : (held ? st : KOB_CX(s1, k));
                             }
                         }
                         float2 Cc[NP], Ss[NP];
@@ -561,22 +566,28 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                         }
                         // store the re-assigned angles of owned cells
                         if (row_owned && mid_lane) {
+                            if (!SEAM) {
 #pragma unroll
-                            for (int k = 0; k < CPL; ++k) {
-                                if (asg[k] && (!SEAM || x + k < a.nx)) {
-                                    const float th = KOB_CX(th2, k);
-                                    const int y = y0 + (int)yrel + 1;
-                                    if (SEAM && (y < GY || y >= a.ny - GY))
-                                        fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
-                                    else {
-                                        float* pth = pthe + k;
-                                        *pth = th;
-                                        if (SEAM) {
+                                for (int k = 0; k < CPL; ++k) {
+                                    if (asg[k]) pthe[k] = KOB_CX(th2, k);
+                                    assigned_any |= asg[k];
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < CPL; ++k) {
+                                    if (asg[k] && x + k < a.nx) {
+                                        const float th = KOB_CX(th2, k);
+                                        const int y = y0 + (int)yrel + 1;
+                                        if (y < GY || y >= a.ny - GY)
+                                            fast_store_edge(a.self.theta, a.lower.theta, a.upper.theta, pitch, a.nx, a.ny, a.lower.ny, x + k, y, th);
+                                        else {
+                                            float* pth = pthe + k;
+                                            *pth = th;
                                             if (x + k < GXR) pth[a.nx] = th;
                                             if (x + k >= a.nx - GXR) pth[-a.nx] = th;
                                         }
+                                        assigned_any = true;
                                     }
-                                    assigned_any = true;
                                 }
                             }
                         }
@@ -647,10 +658,6 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
                     // ---- pass 2 for row y = r-2 (computed unconditionally; stores predicated on the row being owned) ----
                     float2 tu_new[NP];
                     {
-                        const float A_w = __shfl_up_sync(0xffffffffu, A2[NP - 1].y, 1);
-                        const float A_e = __shfl_down_sync(0xffffffffu, A2[0].x, 1);
-                        const float Q_w = __shfl_up_sync(0xffffffffu, Q2[NP - 1].y, 1);
-                        const float Q_e = __shfl_down_sync(0xffffffffu, Q2[0].x, 1);
                         float2 dA[NP], dQ[NP], np_[NP], nt_[NP];
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
