@@ -89,7 +89,7 @@ struct kob_ctx {
     FastMaps maps{};
     int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
     double fast_frac_a = 0.9;
-    int fast_cta_jobs = 1;        // CTA-wide jobs: 8 adjacent strips advance in lock-step (1920 B contiguous per row)
+    int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
@@ -426,7 +426,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
         if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
-        if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));

@@ -42,7 +42,7 @@ struct FastArgs {
     // jobs = nstrips x nseg.  Row segments: nseg_a segments of yj rows, then segments of yj_b rows up to ny
     // (guided scheduling: big jobs first, small jobs last, so that the tail of the dynamic queue is short).
     int nstrips, nseg, yj, nseg_a, yj_b;
-    int cta_jobs;                  // 1: a CTA claims 8 adjacent strips of one segment and keeps its warps in lock-step
+    int cta_jobs;                  // 1/2: a CTA claims 8 adjacent strips of one segment; 1 = always in lock-step, 2 = adaptive
     int nstrips_p;                 // strips padded to a multiple of the warps per CTA (cta_jobs only)
     int no_skip;                   // test knob: never take the far-field (phi == +0) chunk shortcut
     // constants of the far field / held-with-theta==0 cells: eps and eps' at theta = 0
@@ -169,6 +169,7 @@ __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.
 // 1.4 ulp at pi/4 — the class of CUDA's atanf, at half the issue slots because both cells share every FFMA2).
 __device__ __forceinline__ float2 atan01_2(float2 w) {
     const float2 t = f2mul(w, w);
+    // Horner: an Estrin split (depth 4 instead of 7) measured 1.5 % slower — the block is issue-, not chain-limited
     float2 p = f2fma(f2(0.002622196450829506f), t, f2(-0.015132336877286434f));
     p = f2fma(p, t, f2(0.04112152010202408f));
     p = f2fma(p, t, f2(-0.0736667588353157f));
@@ -304,8 +305,14 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
 
         const int nrows = (y1 - y0) + 4;                 // streamed phi rows y0-2 .. y1+1
         const int nch = (nrows + RB - 1) / RB;
+        // CTA-wide jobs: the 8 adjacent strips advance in lock-step (one barrier per chunk) so that a row is fetched as
+        // 1920 contiguous bytes.  cta_jobs == 2: only while none of the 8 does data-dependent work (live theta / seam) —
+        // there the rows take unequal time and the barrier would only add waiting.
+        bool lock = f.cta_jobs == 1;
+        if (f.cta_jobs == 2) lock = !__syncthreads_or((live || seam) && strip < f.nstrips);
         if (strip >= f.nstrips) {                        // padding job (cta_jobs): only keep the CTA's barriers company
-            for (int c = 0; c < nch; ++c) __syncthreads();
+            if (lock)
+                for (int c = 0; c < nch; ++c) __syncthreads();
             continue;
         }
         const int box_x = xs - CPL + GX;                 // padded x of box column 0
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ 
             for (int c = 0; c < nch; ++c) {
                 const unsigned int gi = gchunk + (unsigned int)c;
                 const int st = gi % NST;
-                if (f.cta_jobs) __syncthreads();                                    // adjacent strips advance together
+                if (lock) __syncthreads();                                          // adjacent strips advance together
                 mbar_wait(&bars[st], (gi / NST) & 1u);
                 const float* sp = stages + st * STAGE_FLOATS + CPL * lane + CPL;   // this lane's own phi cells
                 const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
