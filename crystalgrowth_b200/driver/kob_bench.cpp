@@ -4,6 +4,7 @@
 //
 //   kob_bench [--nx 250] [--ny 250] [--dt 1e-4] [--frames 200] [--kernel fast|strict] [--precision f32|f64]
 //             [--anisotropy 6] [--noise 0] [--seed 0] [--nuclei N] [--ppm out.ppm] [--device 0]
+//             [--resume in.kobck] [--save out.kobck] [--checkpoint-every FRAMES]   (long runs: SURVEY §8f rank 4)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +28,8 @@ int main(int argc, char** argv) {
     int nx = 250, ny = 250, frames = 200, device = 0, nuclei = 0;
     double dt = 1e-4, aniso = 6.0, noise = 0.0;
     uint64_t seed = 0;
-    std::string kernel = "fast", precision = "f32", ppm;
+    std::string kernel = "fast", precision = "f32", ppm, resume, save;
+    int ckpt_every = 0;
     for (int i = 1; i < argc; ++i) {
         auto next = [&]() -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", argv[i]); std::exit(2); } return argv[++i]; };
         if (!std::strcmp(argv[i], "--nx")) nx = std::atoi(next());
@@ -42,6 +44,9 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--nuclei")) nuclei = std::atoi(next());
         else if (!std::strcmp(argv[i], "--ppm")) ppm = next();
         else if (!std::strcmp(argv[i], "--device")) device = std::atoi(next());
+        else if (!std::strcmp(argv[i], "--resume")) resume = next();
+        else if (!std::strcmp(argv[i], "--save")) save = next();
+        else if (!std::strcmp(argv[i], "--checkpoint-every")) ckpt_every = std::atoi(next());
         else { std::fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
     }
     try {
@@ -55,11 +60,16 @@ int main(int argc, char** argv) {
             for (int k = 0; k < nuclei; ++k)
                 sim.createNucleus(8 + philox_word(k, seed, 0) % (nx - 16), 8 + philox_word(k, seed, 1) % (ny - 16));
         }
-        sim.iUpdate();                                                // warm-up frame
+        if (!resume.empty()) sim.loadCheckpoint(resume);              // continue a long run exactly where it stopped
+        else sim.iUpdate();                                           // warm-up frame
         sim.sync();
         const auto t0 = std::chrono::steady_clock::now();
-        for (int f = 0; f < frames; ++f) sim.iUpdate();              // the render loop's only simulation call
+        for (int f = 0; f < frames; ++f) {
+            sim.iUpdate();                                            // the render loop's only simulation call
+            if (ckpt_every > 0 && !save.empty() && (f + 1) % ckpt_every == 0) sim.saveCheckpoint(save);
+        }
         sim.sync();
+        if (!save.empty()) sim.saveCheckpoint(save);
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const double cells = (double)nx * ny * 10.0 * frames;
         double solid = 0;

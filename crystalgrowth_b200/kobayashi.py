@@ -74,7 +74,7 @@ class Kobayashi:
             raise KobayashiError(st, msg)
         self.nx, self.ny = int(x), int(y)
         self.ny_global, self.y0 = int(ny_global or y), int(y0)
-        self.precision, self.kernel, self.device = precision, kernel, device
+        self.precision, self.kernel, self.device, self.seed = precision, kernel, device, int(seed)
         self.dtype = np.float64 if prec == KOB_F64 else np.float32
 
     # ---- plumbing ----
@@ -200,6 +200,29 @@ class Kobayashi:
         img = np.empty((self.ny, self.nx, 4), np.uint8)
         self._ck(self._L.kob_render_rgba(self._h, img.ctypes.data_as(C.c_void_p)))
         return img
+
+    # ---- checkpoint / resume (crystalgrowth_b200.checkpoint: KOBCKPT1 files) ----
+    def save_checkpoint(self, path: str):
+        from . import checkpoint as ck
+        p = self.get_params()
+        h = ck.CheckpointHeader(np.dtype(self.dtype).itemsize, self.nx, self.ny, self.ny_global, self.y0, self.step_counter,
+                                self.seed, self.simFrame, tuple(float(getattr(p, k)) for k in ck.PARAM_FIELDS))
+        ck.write_checkpoint(path, h, *self.fields())
+
+    def load_checkpoint(self, path: str):
+        """Restore fields (incl. theta), parameters and the Philox step counter: the continued run is bit-identical
+        to the uninterrupted one."""
+        from . import checkpoint as ck
+        h, phi, t, th = ck.read_checkpoint(path)
+        mine = (np.dtype(self.dtype).itemsize, self.nx, self.ny, self.ny_global, self.y0, self.seed)
+        if (h.elem_bytes, h.nx, h.ny, h.ny_global, h.y0, h.seed) != mine:
+            raise ValueError(f"checkpoint {path} was written for another grid / precision / strip / seed")
+        p = self.get_params()
+        for k, v in zip(ck.PARAM_FIELDS, h.params):
+            setattr(p, k, v)
+        self.set_params(p)
+        self.set_fields(phi, t, th)
+        self.step_counter = h.step_counter
 
     # ---- counters ----
     @property

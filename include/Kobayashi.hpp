@@ -16,6 +16,8 @@
 #define KOBAYASHI_HPP
 
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -34,7 +36,7 @@ class Kobayashi {
 public:
     Kobayashi(int x, int y, float timeStep, int precision = KOB_F32, int kernel = -1, int device = 0,
               uint64_t seed = 0, int64_t ny_global = 0, int64_t y0 = 0)
-        : nx_(x), ny_(y), precision_(precision) {
+        : nx_(x), ny_(y), precision_(precision), seed_(seed), ny_global_(ny_global ? ny_global : y), y0_(y0) {
         kob_params p;
         kob_default_params(&p, static_cast<double>(timeStep));   // float widened, as the reference stores _dt = timeStep
         kob_config c;
@@ -90,6 +92,51 @@ public:
         return img;
     }
 
+    // ---- checkpoint / resume (none in the reference).  File layout, little endian:
+    //   0  char[8]  "KOBCKPT1"          8  u32 header bytes (256), u32 element bytes (4 | 8)
+    //  16  i64 nx, ny, ny_global, y0   48  u64 step counter, u64 Philox seed, i64 sim frame
+    //  72  f64[14] kob_params in declaration order, zero padding to 256, then phi, T, theta (ny*nx each, i + nx*j).
+    // Resuming reproduces the uninterrupted run bit for bit (fields incl. theta, parameters, Philox step counter). ----
+    void saveCheckpoint(const std::string& path) {
+        const size_t e = precision_ == KOB_F64 ? 8u : 4u, n = static_cast<size_t>(nx_) * static_cast<size_t>(ny_);
+        std::vector<unsigned char> buf(3 * n * e);
+        getFields(buf.data(), buf.data() + n * e, buf.data() + 2 * n * e);
+        unsigned char h[256] = {0};
+        std::memcpy(h, "KOBCKPT1", 8);
+        const uint32_t hb = 256, eb = static_cast<uint32_t>(e);
+        std::memcpy(h + 8, &hb, 4); std::memcpy(h + 12, &eb, 4);
+        const int64_t dims[4] = {nx_, ny_, ny_global_, y0_};
+        std::memcpy(h + 16, dims, 32);
+        const uint64_t sc = stepCounter();
+        const int64_t fr = simFrame();
+        std::memcpy(h + 48, &sc, 8); std::memcpy(h + 56, &seed_, 8); std::memcpy(h + 64, &fr, 8);
+        const kob_params p = params();
+        static_assert(sizeof(kob_params) == 14 * sizeof(double), "kob_params layout");
+        std::memcpy(h + 72, &p, sizeof p);
+        FILE* fp = std::fopen(path.c_str(), "wb");
+        if (!fp) throw KobayashiError(KOB_ERR_INVALID_ARG, "cannot open " + path + " for writing");
+        const bool ok = std::fwrite(h, 1, 256, fp) == 256 && std::fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
+        if (std::fclose(fp) != 0 || !ok) throw KobayashiError(KOB_ERR_INVALID_ARG, "short write to " + path);
+    }
+    void loadCheckpoint(const std::string& path) {
+        FILE* fp = std::fopen(path.c_str(), "rb");
+        if (!fp) throw KobayashiError(KOB_ERR_INVALID_ARG, "cannot open " + path);
+        unsigned char h[256];
+        const size_t e = precision_ == KOB_F64 ? 8u : 4u, n = static_cast<size_t>(nx_) * static_cast<size_t>(ny_);
+        std::vector<unsigned char> buf(3 * n * e);
+        const bool ok = std::fread(h, 1, 256, fp) == 256 && std::fread(buf.data(), 1, buf.size(), fp) == buf.size();
+        std::fclose(fp);
+        uint32_t hb, eb; int64_t dims[4]; uint64_t sc, seed; kob_params p;
+        std::memcpy(&hb, h + 8, 4); std::memcpy(&eb, h + 12, 4); std::memcpy(dims, h + 16, 32);
+        std::memcpy(&sc, h + 48, 8); std::memcpy(&seed, h + 56, 8); std::memcpy(&p, h + 72, sizeof p);
+        if (!ok || std::memcmp(h, "KOBCKPT1", 8) != 0 || hb != 256) throw KobayashiError(KOB_ERR_INVALID_ARG, path + " is not a KOBCKPT1 checkpoint");
+        if (eb != e || dims[0] != nx_ || dims[1] != ny_ || dims[2] != ny_global_ || dims[3] != y0_ || seed != seed_)
+            throw KobayashiError(KOB_ERR_INVALID_ARG, "checkpoint " + path + " was written for another grid / precision / strip / seed");
+        setParams(p);
+        setFields(buf.data(), buf.data() + n * e, buf.data() + 2 * n * e);
+        ck(kob_set_step_counter(ctx_, sc), "kob_set_step_counter");
+    }
+
     // ---- bookkeeping (_simTime, _simFrame, src/Kobayashi.cpp:237-238) ----
     int64_t simFrame() const { int64_t f = 0; ck(kob_sim_frame(ctx_, &f), "kob_sim_frame"); return f; }
     double simTimeMs() const { double ms = 0; ck(kob_sim_time_ms(ctx_, &ms), "kob_sim_time_ms"); return ms; }
@@ -112,6 +159,8 @@ private:
     }
     kob_ctx* ctx_ = nullptr;
     int nx_, ny_, precision_;
+    uint64_t seed_;
+    int64_t ny_global_, y0_;
     bool updateFlag_ = true;
 };
 
