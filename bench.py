@@ -168,10 +168,6 @@ def run_reference_arm(a, rank):
     print(json.dumps(line), flush=True)
 
 
-def sim_y0(ring):
-    return getattr(ring, "y0", 0)
-
-
 def workload_config(a, world):
     if a.strong:
         return {"workload": f"{a.strong}x{a.strong} torus strong-scaled over {world} GPU(s) ({a.strong}x{a.strong // world} cells per GPU), "
@@ -240,7 +236,7 @@ def main():
     sim = ring.strip
     ring.seed_nuclei(nuclei_positions(a.nuclei * (16 if a.strong else world), nx, nyg, SEED))
     if a.field == "dense":
-        sim.set_fields(*dense_state(nx, ring.ny, sim_y0(ring)), None)
+        sim.set_fields(*dense_state(nx, ring.ny, ring.y0), None)
         ring.refresh()
     cells_per_step = nx * ring.ny * a.substeps            # this rank
     total_cells_per_step = nx * nyg * a.substeps
@@ -283,7 +279,6 @@ def main():
         saved = sim.fields()
         ctr = sim.step_counter
         sim.set_fields(*dense_state(nx, ring.ny, 0), np.zeros((ring.ny, nx), np.float32))
-        del_ms = None
         sim.step(3 * a.substeps)
         sim.sync()
         d_steps = 5

@@ -7,8 +7,10 @@
 // cos(j*theta), sin(j*theta) = Re/Im ((gx + i gy)/|g|)^j — one rsqrt and a few FMAs instead of div+atan+sin+cos.
 //
 // Structure (B200-first):
-//   * persistent grid, one warp = one independent worker; workers pull jobs (column strip x row segment) from a
-//     global counter.  There is NO __syncthreads in the steady state.
+//   * persistent grid; a CTA claims 8 adjacent column strips of one row segment from a global counter and hands one
+//     strip to each warp, which then works on its own (TMA ring, registers, stores).  Far-field CTA jobs keep their
+//     warps in lock-step (one barrier per chunk) so that a grid row is fetched as 1920 contiguous bytes; jobs with
+//     data-dependent work free-run.  (cta_jobs = 0 falls back to per-warp jobs with no barrier at all.)
 //   * every worker owns a ring of NST shared-memory stages fed by TMA (cp.async.bulk.tensor.2d + mbarrier
 //     complete_tx): a stage carries RB rows of phi and the RB rows of T one row behind it.  Loads are issued
 //     NST chunks ahead by one lane; no LSU instruction or register is spent on input traffic.
@@ -20,6 +22,10 @@
 //     every alias (own ghost columns, neighbour strips' ghost rows — peer memory over NVLink when P > 1).
 //   * theta traffic is predicated: read only where the hold rule fires inside blocks flagged "theta may be
 //     non-zero", written only where the state machine re-assigns it.
+//   * far-field shortcut: a chunk whose phi rows (and the 4 rows before them) are all +0 only diffuses T — bit-identical
+//     to the full path, and what makes sparse (seeded) fields purely HBM bound.
+//   * the data-dependent block (angle, anisotropy, m(T), noise) is packed f32x2 as well: one minimax atan polynomial
+//     serves both the angle and m(T); the Philox4x32-10 block of 4 cells is drawn once per lane pair.
 #ifndef KOB_FAST_CUH
 #define KOB_FAST_CUH
 
@@ -123,28 +129,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
             smem_u32(dst)),
         "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
-}
-
-// (c + i s)^J by square-and-multiply, J a compile-time constant.
-template <int J>
-__device__ __forceinline__ void cpow(float c, float s, float& C, float& S) {
-    if (J == 0) { C = 1.0f; S = 0.0f; return; }
-    if (J == 1) { C = c; S = s; return; }
-    float hc, hs;
-    cpow<J / 2>(c, s, hc, hs);
-    float qc = fmaf(hc, hc, -hs * hs), qs = 2.0f * hc * hs;
-    if (J & 1) { C = fmaf(qc, c, -qs * s); S = fmaf(qc, s, qs * c); }
-    else { C = qc; S = qs; }
-}
-__device__ __forceinline__ void cpow_rt(int j, float c, float s, float& C, float& S) {   // 0 <= j <= 16, warp-uniform
-    float rc = 1.0f, rs = 0.0f;
-#pragma unroll
-    for (int bit = 4; bit >= 0; --bit) {
-        const float qc = fmaf(rc, rc, -rs * rs), qs = 2.0f * rc * rs;
-        rc = qc; rs = qs;
-        if ((j >> bit) & 1) { const float tc = fmaf(rc, c, -rs * s), ts = fmaf(rc, s, rs * c); rc = tc; rs = ts; }
-    }
-    C = rc; S = rs;
 }
 
 // ---- packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two cells per issue slot) -----------------
