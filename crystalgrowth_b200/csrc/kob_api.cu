@@ -27,7 +27,7 @@ struct Layout {
     size_t elem;
     long long pitch, rows;
     int nfbx, nfby;
-    size_t field_bytes, off_phi[2], off_t[2], off_theta, off_flags, off_arrive, off_ticket, total;
+    size_t field_bytes, off_phi[2], off_t[2], off_theta[2], off_flags, off_arrive, off_ticket, total;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -45,7 +45,8 @@ Layout make_layout(int64_t nx, int64_t ny, int prec) {
     L.off_phi[1] = o; o += L.field_bytes;
     L.off_t[0] = o; o += L.field_bytes;
     L.off_t[1] = o; o += L.field_bytes;
-    L.off_theta = o; o += L.field_bytes;
+    L.off_theta[0] = o; o += L.field_bytes;
+    L.off_theta[1] = o; o += L.field_bytes;
     L.off_flags = o; o += align_up((size_t)L.nfbx * L.nfby * 4, 256);
     L.off_arrive = o; o += 256;
     L.off_ticket = o; o += 256;
@@ -75,6 +76,7 @@ struct kob_ctx {
     uint64_t seed = 0, step = 0;
     uint32_t epoch = 0;
     int cur = 0;
+    int tcur = 0;                 // which theta buffer is current (flipped by every two-step launch)
     kob_params params{};
     Layout L{};
     char* base = nullptr;
@@ -116,13 +118,14 @@ int fail(kob_ctx* c, int code, const std::string& msg) {
 #define KOB_DISPATCH(c, fn, ...) ((c)->prec == KOB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 template <typename real>
-StripView<real> view_of(char* base, const Layout& L, long long ny) {
+StripView<real> view_of(char* base, const Layout& L, long long ny, int tcur) {
     StripView<real> v;
     v.phi[0] = reinterpret_cast<real*>(base + L.off_phi[0]);
     v.phi[1] = reinterpret_cast<real*>(base + L.off_phi[1]);
     v.t[0] = reinterpret_cast<real*>(base + L.off_t[0]);
     v.t[1] = reinterpret_cast<real*>(base + L.off_t[1]);
-    v.theta = reinterpret_cast<real*>(base + L.off_theta);
+    v.theta = reinterpret_cast<real*>(base + L.off_theta[tcur]);
+    v.theta_next = reinterpret_cast<real*>(base + L.off_theta[tcur ^ 1]);
     v.tflags = reinterpret_cast<uint32_t*>(base + L.off_flags);
     v.arrive = reinterpret_cast<uint32_t*>(base + L.off_arrive);
     v.ny = ny;
@@ -154,10 +157,10 @@ KParams<real> kparams_of(const kob_params& p) {
 template <typename real>
 StepArgs<real> args_of(kob_ctx* c) {
     StepArgs<real> a;
-    a.self = view_of<real>(c->base, c->L, c->ny);
+    a.self = view_of<real>(c->base, c->L, c->ny, c->tcur);
     const Layout Ll = make_layout(c->nx, c->lower.ny, c->prec), Lu = make_layout(c->nx, c->upper.ny, c->prec);
-    a.lower = view_of<real>(c->lower.base, Ll, c->lower.ny);
-    a.upper = view_of<real>(c->upper.base, Lu, c->upper.ny);
+    a.lower = view_of<real>(c->lower.base, Ll, c->lower.ny, c->tcur);   // all strips of a ring run the same launch sequence
+    a.upper = view_of<real>(c->upper.base, Lu, c->upper.ny, c->tcur);
     a.prm = kparams_of<real>(c->params);
     a.noise_field = c->noise_field;
     a.seed = c->seed; a.step = c->step;
@@ -196,11 +199,12 @@ int build_fast_maps(kob_ctx* c) {
     return KOB_OK;
 }
 
-constexpr int FAST_WARPS = 8;
+
 
 template <int NP, int JM, bool NOISE, bool ROT>
 int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     auto kern = kob_step_fast<NP, JM, NOISE, ROT>;
+    constexpr int FAST_WARPS = fast_warps<NP>();
     const int smem = FAST_WARPS * fast_warp_bytes<NP>() + FAST_WARPS * FAST_NST * 8;
     static int ctas_per_sm[64] = {0};   // per device
     int& cps = ctas_per_sm[c->device & 63];
@@ -333,7 +337,7 @@ int set_device(kob_ctx* c) {
 }
 
 int zero_fields(kob_ctx* c) {
-    // phi[2], T[2], theta, theta flags: one contiguous range
+    // phi[2], T[2], theta[2], theta flags: one contiguous range
     KOB_CUDA(c, cudaMemsetAsync(c->base, 0, c->L.off_arrive, c->stream));
     return KOB_OK;
 }
@@ -540,7 +544,7 @@ int kob_get_fields(kob_ctx* c, void* phi, void* t, void* angl) {
     const size_t o = ((size_t)GY * c->L.pitch + GX) * e;
     if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(phi, w, c->base + c->L.off_phi[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
     if (t) KOB_CUDA(c, cudaMemcpy2DAsync(t, w, c->base + c->L.off_t[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
-    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(angl, w, c->base + c->L.off_theta + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
+    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(angl, w, c->base + c->L.off_theta[c->tcur] + o, sp, w, c->ny, cudaMemcpyDeviceToHost, c->stream));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
     return check_fault(c);
 }
@@ -552,7 +556,11 @@ int kob_set_fields(kob_ctx* c, const void* phi, const void* t, const void* angl)
     const size_t o = ((size_t)GY * c->L.pitch + GX) * e;
     if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_phi[c->cur] + o, sp, phi, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
     if (t) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_t[c->cur] + o, sp, t, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
-    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_theta + o, sp, angl, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
+    if (angl) {
+        KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_theta[c->tcur] + o, sp, angl, w, w, c->ny, cudaMemcpyHostToDevice, c->stream));
+        // the two-step kernel only writes non-zero angles into the other buffer: it must not hold stale ones
+        KOB_CUDA(c, cudaMemsetAsync(c->base + c->L.off_theta[c->tcur ^ 1], 0, c->L.field_bytes, c->stream));
+    }
     KOB_TRY(KOB_DISPATCH(c, refresh_impl, c));
     if (angl) KOB_TRY(KOB_DISPATCH(c, rebuild_flags_impl, c));
     return KOB_OK;

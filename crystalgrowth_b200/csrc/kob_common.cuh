@@ -2,8 +2,9 @@
 //
 // HBM layout of one strip (one context = one GPU's rows [y0, y0+ny) of the nx x ny_global torus):
 //
-//   padded row:   | GX=4 ghost cols (only the inner 2 used) | nx cells | 2 ghost cols | pad to 32 elems |
-//   padded array: | GY=2 ghost rows | ny rows | GY=2 ghost rows |
+//   padded row:   | GX=4 ghost cols | nx cells | GXR=4 ghost cols | pad to 32 elems |
+//   padded array: | GY=4 ghost rows | ny rows | GY=4 ghost rows |
+// (the single-step kernels read ghosts to depth 2; the two-step kernel, whose composed stencil has radius 4, to depth 4)
 //
 // phi and T are double buffered (Jacobi step: read `cur`, write `cur^1`); theta is single buffered and
 // updated in place (a cell's theta is either re-assigned — then nobody reads the old value — or held —
@@ -24,8 +25,8 @@
 namespace kob {
 
 constexpr int GX = 4;    // ghost columns on the left (keeps the interior 16/32-byte aligned)
-constexpr int GXR = 2;   // ghost columns on the right
-constexpr int GY = 2;    // ghost rows per side
+constexpr int GXR = 4;   // ghost columns on the right
+constexpr int GY = 4;    // ghost rows per side
 constexpr int FBX = 128; // theta-flag block, padded coordinates
 constexpr int FBY = 32;
 
@@ -34,7 +35,8 @@ template <typename real>
 struct StripView {
     real* phi[2];
     real* t[2];
-    real* theta;
+    real* theta;        // the current angle buffer (single-step kernels update it in place)
+    real* theta_next;   // the other one: the two-step kernel reads `theta` and writes `theta_next`, then they swap
     uint32_t* tflags;   // [nfby][nfbx] : 1 = some theta in this block of the padded array may be non-zero
     uint32_t* arrive;   // [3]: arrive[0] written by the lower neighbour, arrive[1] by the upper neighbour,
                         //      arrive[2] = fault word (set when a wait on a neighbour timed out)

@@ -206,8 +206,16 @@ __device__ __noinline__ void fast_mark_flags(uint32_t* self_f, uint32_t* lower_f
 }
 
 // JM: 4 / 6 = compile-time integer mode, 0 = run-time integer mode (prm.jmode in 0..16), -1 = any real j (trig).
+// NP = 1: 8 warps x 2 CTAs per SM at <= 128 registers.  NP = 2 (4 cells per lane) needs ~2x the register windows: 12 warps
+// x 1 CTA per SM at <= 168 registers.
+#ifndef KOB_FAST_WARPS2
+#define KOB_FAST_WARPS2 12
+#endif
+template <int NP>
+__host__ __device__ constexpr int fast_warps() { return NP == 2 ? KOB_FAST_WARPS2 : 8; }
+
 template <int NP, int JM, bool NOISE, bool ROT>
-__global__ void __launch_bounds__(256, 2) kob_step_fast(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
+__global__ void __launch_bounds__(32 * fast_warps<NP>(), NP == 2 ? 1 : 2) kob_step_fast(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
                                                          const FastArgs f) {
     using G = FastGeom<NP>;
     constexpr int CPL = G::CPL, BW = G::BW, RB = FAST_RB, NST = FAST_NST;
