@@ -15,6 +15,7 @@
 #include "kob_aux.cuh"
 #include "kob_common.cuh"
 #include "kob_fast.cuh"
+#include "kob_fast2.cuh"
 #include "kob_strict.cuh"
 
 using namespace kob;
@@ -88,11 +89,13 @@ struct kob_ctx {
     bool linked = false;
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
-    FastMaps maps{};
+    FastMaps maps{}, maps2{};
     int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
     double fast_frac_a = 0.9;
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
+    int fast2 = 0;                // two sub-steps per launch where kob_step(n >= 2) allows it (KOB_FAST2)
+    int fast2_yj = 128, fast2_yj_b = 32;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
@@ -190,10 +193,16 @@ int build_fast_maps(kob_ctx* c) {
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap* maps[4] = {&c->maps.phi[0], &c->maps.phi[1], &c->maps.t[0], &c->maps.t[1]};
     const size_t offs[4] = {c->L.off_phi[0], c->L.off_phi[1], c->L.off_t[0], c->L.off_t[1]};
+    const cuuint32_t box2[2] = {(cuuint32_t)F2_BW, (cuuint32_t)FAST_RB};       // the two-step kernel's wider box
+    CUtensorMap* maps2[4] = {&c->maps2.phi[0], &c->maps2.phi[1], &c->maps2.t[0], &c->maps2.t[1]};
     for (int i = 0; i < 4; ++i) {
         CUresult r = enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = enc(maps2[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box2, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     }
     return KOB_OK;
@@ -234,7 +243,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     return KOB_OK;
 }
 
-int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
+FastArgs fast_args_of(kob_ctx* c, const StepArgs<float>& a) {
     const KParams<float>& P = a.prm;
     FastArgs f{};
     f.job_ctr = reinterpret_cast<unsigned long long*>(c->base + c->L.off_ticket + 8);
@@ -258,6 +267,72 @@ int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
     }
     f.pc2 = (uint32_t)a.step;
     f.pc3 = (uint32_t)(a.step >> 32);
+    f.ny_global = c->ny_global;
+    return f;
+}
+
+// ---- two sub-steps per launch (kob_fast2.cuh) ----
+template <int JM, bool NOISE, bool ROT>
+int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
+    auto kern = kob_step_fast2<JM, NOISE, ROT>;
+    const int smem = F2_WARPS * F2_WARP_BYTES + F2_WARPS * FAST_NST * 8;
+    static int ctas_per_sm[64] = {0};   // per device
+    int& cps = ctas_per_sm[c->device & 63];
+    if (cps == 0) {
+        KOB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, F2_WARPS * 32, smem));
+        if (cps < 1) return fail(c, KOB_ERR_CUDA, "two-step FAST kernel does not fit on an SM");
+    }
+    int nsm = 0;
+    KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    f.nstrips = (int)((c->nx + F2_OUTC - 1) / F2_OUTC);
+    f.yj = c->fast2_yj;
+    f.yj_b = std::min(c->fast2_yj_b, c->fast2_yj);
+    f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
+    if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
+    const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
+    f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
+    f.cta_jobs = 2;
+    f.no_skip = c->fast_no_skip;
+    f.nstrips_p = (f.nstrips + F2_WARPS - 1) / F2_WARPS * F2_WARPS;
+    const long long njobs = (long long)f.nstrips_p * f.nseg;
+    const int grid = (int)std::min<long long>((long long)nsm * cps, njobs / F2_WARPS);
+    f.job_base = c->job_expected;
+    kern<<<grid, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+    c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * F2_WARPS;   // every CTA overshoots once
+    return KOB_OK;
+}
+
+// Can the next two sub-steps go through the two-step kernel?
+bool fast2_eligible(const kob_ctx* c) {
+    return c->kernel == KOB_KERNEL_FAST && c->prec == KOB_F32 && c->fast2 && c->fast_np == 1 && !c->noise_field &&
+           c->nx >= 8 && c->ny >= 8;
+}
+
+int launch_two_steps_fast(kob_ctx* c) {
+    const StepArgs<float> a = args_of<float>(c);
+    const KParams<float>& P = a.prm;
+    const FastArgs f = fast_args_of(c, a);
+    const bool noise = c->params.noise_a != 0.0;
+    const bool rot = P.theta0 != 0.0f;
+    const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
+#define KOB_FAST2_CASE(JM_, ROT_) \
+    do { KOB_TRY((noise ? launch_fast2_t<JM_, true, ROT_>(c, a, f) : launch_fast2_t<JM_, false, ROT_>(c, a, f))); } while (0)
+    if (jm == 4) KOB_FAST2_CASE(4, false);
+    else if (jm == 6) KOB_FAST2_CASE(6, false);
+    else if (jm == 0 && !rot) KOB_FAST2_CASE(0, false);
+    else if (jm == 0 && rot) KOB_FAST2_CASE(0, true);
+    else KOB_FAST2_CASE(-1, false);
+#undef KOB_FAST2_CASE
+    KOB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    c->cur ^= 1; c->tcur ^= 1; c->step += 2; c->epoch += 1;
+    return KOB_OK;
+}
+
+int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
+    const KParams<float>& P = a.prm;
+    FastArgs f = fast_args_of(c, a);
     const bool rot = P.theta0 != 0.0f;
     const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
 #define KOB_FAST_CASE(NP_, JM_, ROT_)                                                          \
@@ -432,6 +507,9 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST2_YJ")) c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));
         int rcm = build_fast_maps(c);
@@ -497,7 +575,9 @@ int kob_get_params(const kob_ctx* c, kob_params* p) {
 int kob_step(kob_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
-    for (int64_t s = 0; s < nsteps; ++s) KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
+    int64_t s = 0;
+    while (nsteps - s >= 2 && fast2_eligible(c)) { KOB_TRY(launch_two_steps_fast(c)); s += 2; }   // temporal blocking
+    for (; s < nsteps; ++s) KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
     return KOB_OK;
 }
 

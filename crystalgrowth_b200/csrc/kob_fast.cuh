@@ -60,12 +60,12 @@ struct FastArgs {
     float m_off;                   // (alpha/PI_F) * pi/2: m(T) for |gamma (T_eq - T)| -> inf
     uint32_t pk[20];               // Philox round keys: pk[2r] = seed_lo + r*W0, pk[2r+1] = seed_hi + r*W1
     uint32_t pc2, pc3;             // Philox counter words 2, 3 = (step_lo, step_hi)
+    long long ny_global;           // rows of the whole torus (two-step kernel: noise of wrapped ghost rows)
 };
 
 // Philox4x32-10 with the per-round keys (key + r * Weyl) precomputed on the host into the constant bank and the
 // (step_lo, step_hi) half of the counter taken from there too.  Same bits as kob_math.h's philox4x32_10.
-__device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, uint32_t c1) {
-    uint32_t c2 = f.pc2, c3 = f.pc3;
+__device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
@@ -77,6 +77,7 @@ __device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, u
     o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
     return o;
 }
+__device__ __forceinline__ Philox4 fast_philox(const FastArgs& f, uint32_t c0, uint32_t c1) { return fast_philox(f, c0, c1, f.pc2, f.pc3); }
 
 template <int NP>
 struct FastGeom {
