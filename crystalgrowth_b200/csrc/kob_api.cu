@@ -95,7 +95,7 @@ struct kob_ctx {
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
     int fast2 = 0;                // two sub-steps per launch where kob_step(n >= 2) allows it (KOB_FAST2)
-    int fast2_yj = 128, fast2_yj_b = 32;
+    int fast2_yj = 128, fast2_yj_b = 32, fast2_lock = 2;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
@@ -275,7 +275,7 @@ FastArgs fast_args_of(kob_ctx* c, const StepArgs<float>& a) {
 template <int JM, bool NOISE, bool ROT>
 int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     auto kern = kob_step_fast2<JM, NOISE, ROT>;
-    const int smem = F2_WARPS * F2_WARP_BYTES + F2_WARPS * FAST_NST * 8;
+    const int smem = F2_WARPS * F2_WARP_BYTES + F2_WARPS * F2_NST * 8;
     static int ctas_per_sm[64] = {0};   // per device
     int& cps = ctas_per_sm[c->device & 63];
     if (cps == 0) {
@@ -292,14 +292,14 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
     const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
     f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
-    f.cta_jobs = 2;
+    f.cta_jobs = c->fast2_lock;
     f.no_skip = c->fast_no_skip;
     f.nstrips_p = (f.nstrips + F2_WARPS - 1) / F2_WARPS * F2_WARPS;
-    const long long njobs = (long long)f.nstrips_p * f.nseg;
-    const int grid = (int)std::min<long long>((long long)nsm * cps, njobs / F2_WARPS);
+    const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
+    const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + F2_WARPS - 1) / F2_WARPS);
     f.job_base = c->job_expected;
     kern<<<grid, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
-    c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * F2_WARPS;   // every CTA overshoots once
+    c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * F2_WARPS;   // every warp / CTA overshoots once
     return KOB_OK;
 }
 
@@ -510,6 +510,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_LOCK")) c->fast2_lock = std::min(2, std::max(0, std::atoi(e_)));   // 0 per-warp jobs, 1 CTA jobs, 2 CTA jobs in lock-step
         if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));
         int rcm = build_fast_maps(c);

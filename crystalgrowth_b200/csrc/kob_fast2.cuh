@@ -25,11 +25,18 @@ namespace kob {
 
 constexpr int F2_OUTC = 56;     // output columns per strip (lanes 2..29)
 constexpr int F2_HALO = 4;      // pass-1 columns left of the first output column (lanes 0, 1)
-constexpr int F2_WARPS = 8;
+#ifndef KOB_F2_WARPS
+#define KOB_F2_WARPS 8
+#endif
+#ifndef KOB_F2_NST
+#define KOB_F2_NST 8
+#endif
+constexpr int F2_WARPS = KOB_F2_WARPS;
+constexpr int F2_NST = KOB_F2_NST;   // TMA stages per warp (one CTA per SM: a deeper ring than the single-step kernel's)
 constexpr int F2_BW = 72;       // TMA box width: columns xs-4 .. xs+67 (the box must start on a 16-byte boundary)
 constexpr int F2_BOX_FLOATS = (FAST_RB * F2_BW + 31) / 32 * 32;
 constexpr int F2_STAGE_FLOATS = 2 * F2_BOX_FLOATS;
-constexpr int F2_WARP_BYTES = FAST_NST * F2_STAGE_FLOATS * 4;
+constexpr int F2_WARP_BYTES = F2_NST * F2_STAGE_FLOATS * 4;
 
 // Register windows of one level; "r" is the phi row this level consumes in the current iteration.
 struct F2Level {
@@ -244,7 +251,7 @@ __device__ __forceinline__ void f2_row(F2Level& S, const F2Const& C, const KPara
 template <int JM, bool NOISE, bool ROT>
 __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
                                                                   const FastArgs f) {
-    constexpr int BW = F2_BW, RB = FAST_RB, NST = FAST_NST;
+    constexpr int BW = F2_BW, RB = FAST_RB, NST = F2_NST;
     constexpr int STAGE_FLOATS = F2_STAGE_FLOATS, BOX_FLOATS = F2_BOX_FLOATS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -271,15 +278,24 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
     unsigned int gchunk = 0;
 
     __shared__ unsigned long long s_job;
-    const int njobs_q = f.nstrips_p * f.nseg;
+    const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
+    const int njobs_q = nsp * f.nseg;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
-        __syncthreads();
-        if (s_job >= (unsigned long long)njobs_q) break;
-        const int job = (int)(s_job + (unsigned long long)warp);
-        const int strip = job - (job / f.nstrips_p) * f.nstrips_p;
-        const int sq = job / f.nstrips_p;
+        unsigned long long jraw = 0;
+        if (f.cta_jobs) {                                    // a CTA claims 8 adjacent strips of one segment
+            __syncthreads();
+            if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+            __syncthreads();
+            if (s_job >= (unsigned long long)njobs_q) break;
+            jraw = s_job + (unsigned long long)warp;
+        } else {                                             // every warp claims its own job: no barrier anywhere
+            if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
+            jraw = __shfl_sync(0xffffffffu, jraw, 0);
+            if (jraw >= (unsigned long long)njobs_q) break;
+        }
+        const int job = (int)jraw;
+        const int strip = job - (job / nsp) * nsp;
+        const int sq = job / nsp;
         const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);     // the two torus-seam segments first
         const int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
         const int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         }
         const bool live = livemask != 0u;
         const bool seam = strip == 0 || (strip + 1) * F2_OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
-        const bool lock = !__syncthreads_or((live || seam) && real_job);        // far-field CTA jobs advance in lock-step
+        const bool lock = f.cta_jobs == 2 && !__syncthreads_or((live || seam) && real_job);   // far-field CTA jobs advance in lock-step
 
         const int nrows = (y1 - y0) + 8;                 // streamed phi^0 rows y0-4 .. y1+3
         const int nch = (nrows + RB - 1) / RB;
