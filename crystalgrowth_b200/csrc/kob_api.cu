@@ -95,7 +95,9 @@ struct kob_ctx {
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
     int fast2 = 0;                // two sub-steps per launch where kob_step(n >= 2) allows it (KOB_FAST2)
-    int fast2_yj = 128, fast2_yj_b = 32, fast2_lock = 2;
+    int fast2_yj = 96, fast2_yj_b = 32, fast2_lock = 0, fast2_far = 1, fast2_far_cta = 1;
+    int* worklist = nullptr;      // far/general launch pair: [count, claim, -, -, job ids ...]
+    long long worklist_cap = 0;
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
@@ -296,6 +298,36 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     f.no_skip = c->fast_no_skip;
     f.nstrips_p = (f.nstrips + F2_WARPS - 1) / F2_WARPS * F2_WARPS;
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
+    if (c->fast2_far && !f.cta_jobs) {
+        // far/general launch pair: the light far pass visits every job and leaves the rest on the work list
+        if (c->worklist_cap < njobs) {
+            if (c->worklist) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->worklist); c->worklist = nullptr; }
+            KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(4 * njobs + 4) * sizeof(int)));
+            c->worklist_cap = njobs;
+        }
+        unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim
+        KOB_CUDA(c, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), c->stream));
+        static int far_cps[64] = {0};
+        int& fcps = far_cps[c->device & 63];
+        const int far_smem = FAR2_WARPS * FAR2_WARP_BYTES + FAR2_WARPS * FAR2_NST * 8;
+        if (fcps == 0) {
+            KOB_CUDA(c, cudaFuncSetAttribute(kob_far2, cudaFuncAttributeMaxDynamicSharedMemorySize, far_smem));
+            KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fcps, kob_far2, FAR2_WARPS * 32, far_smem));
+            if (fcps < 1) return fail(c, KOB_ERR_CUDA, "far-pass kernel does not fit on an SM");
+        }
+        Far2Args w{c->worklist + 4, counters};
+        FastArgs ff = f;
+        ff.cta_jobs = c->fast2_far_cta;
+        const long long fjobs = (long long)(ff.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
+        ff.job_base = c->job_expected;
+        const int fgrid = (int)std::min<long long>((long long)nsm * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
+        kob_far2<<<fgrid, FAR2_WARPS * 32, far_smem, c->stream>>>(c->maps2, a, ff, w);
+        c->job_expected += (unsigned long long)fjobs + (unsigned long long)fgrid * FAR2_WARPS;
+        c->launches += 1;
+        f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;
+        kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+        return KOB_OK;
+    }
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + F2_WARPS - 1) / F2_WARPS);
     f.job_base = c->job_expected;
     kern<<<grid, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
@@ -510,6 +542,8 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_LOCK")) c->fast2_lock = std::min(2, std::max(0, std::atoi(e_)));   // 0 per-warp jobs, 1 CTA jobs, 2 CTA jobs in lock-step
         if (const char* e_ = std::getenv("KOB_FAST_YJB")) c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_FRAC")) c->fast_frac_a = std::min(1.0, std::max(0.0, std::atof(e_)));
@@ -531,6 +565,7 @@ int kob_destroy(kob_ctx* c) {
     if (c->upper.ipc && c->upper.base && c->upper.base != c->lower.base) cudaIpcCloseMemHandle(c->upper.base);
     if (c->noise_field) cudaFree(c->noise_field);
     if (c->rgba) cudaFree(c->rgba);
+    if (c->worklist) cudaFree(c->worklist);
     if (c->base) cudaFree(c->base);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -61,6 +61,10 @@ struct FastArgs {
     uint32_t pk[20];               // Philox round keys: pk[2r] = seed_lo + r*W0, pk[2r+1] = seed_hi + r*W1
     uint32_t pc2, pc3;             // Philox counter words 2, 3 = (step_lo, step_hi)
     long long ny_global;           // rows of the whole torus (two-step kernel: noise of wrapped ghost rows)
+    // two-step kernel, general pass: jobs come from the work list the far pass wrote (nullptr: all jobs, from job_ctr)
+    const int* list;
+    const unsigned int* list_count;
+    unsigned int* list_claim;
 };
 
 // Philox4x32-10 with the per-round keys (key + r * Weyl) precomputed on the host into the constant bank and the

@@ -248,6 +248,198 @@ __device__ __forceinline__ void f2_row(F2Level& S, const F2Const& C, const KPara
     S.Q2 = Qn;
 }
 
+// ---- far pass --------------------------------------------------------------------------------------------------
+// The two-step kernel needs ~230 registers (two sets of windows + the data-dependent block), i.e. 8 warps per SM — too
+// few to keep HBM busy on the far-field rows, which need almost none of that state.  So a launch pair is used:
+//   1. kob_far2 (this kernel, ~48 registers, 24 warps per SM) visits EVERY job.  Interior jobs whose theta flags are
+//      clear are streamed (seam jobs too, with alias stores); as long as every phi^0 chunk seen so far is all +0 the rows only diffuse T (twice, level 2
+//      from level 1's rows in registers) — the same instructions as kob_step_fast2's shortcut, bit for bit.  A job that
+//      is on a seam, has live theta, or meets a non-zero phi chunk is appended to the work list instead (rows already
+//      stored are valid — they depend only on rows seen to be zero — and will simply be stored again).
+//   2. kob_step_fast2 then processes the work list.
+struct Far2Args {
+    int* list;                  // job ids for the general pass
+    unsigned int* list_count;   // entries appended by this launch (zeroed by the host before it)
+};
+
+constexpr int FAR2_WARPS = 8;
+constexpr int FAR2_NST = 4;
+constexpr int FAR2_WARP_BYTES = FAR2_NST * F2_STAGE_FLOATS * 4;
+
+__global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
+                                                              const FastArgs f, const Far2Args w) {
+    constexpr int BW = F2_BW, RB = FAST_RB, NST = FAR2_NST;
+    constexpr int STAGE_FLOATS = F2_STAGE_FLOATS, BOX_FLOATS = F2_BOX_FLOATS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* stages = reinterpret_cast<float*>(smem_raw) + (size_t)warp * NST * STAGE_FLOATS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * FAR2_WARP_BYTES) + warp * NST;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const CUtensorMap* map_phi = a.cur ? &maps.phi[1] : &maps.phi[0];
+    const CUtensorMap* map_t = a.cur ? &maps.t[1] : &maps.t[0];
+    float* __restrict__ phi_out = a.self.phi[a.cur ^ 1];
+    float* __restrict__ t_out = a.self.t[a.cur ^ 1];
+    const long long pitch = a.pitch;
+    F2Const C;
+    C.idx2 = C.idy2 = C.il2 = C.dtt2 = C.B02 = f2(0.f);
+    C.ildt2 = f2(f.il_dt); C.K2 = f2(a.prm.K);
+    C.A0 = 0.f; C.e = 0.f; C.pi = 0.f;
+    unsigned int gchunk = 0;
+    __shared__ unsigned long long s_job;
+    const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
+    const int njobs_q = nsp * f.nseg;
+    for (;;) {
+        unsigned long long jraw = 0;
+        if (f.cta_jobs) {                                    // a CTA claims 8 adjacent strips and keeps them in lock-step:
+            __syncthreads();                                 // a grid row is then fetched as 8 x 224 contiguous bytes
+            if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+            __syncthreads();
+            if (s_job >= (unsigned long long)njobs_q) break;
+            jraw = s_job + (unsigned long long)warp;
+        } else {
+            if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
+            jraw = __shfl_sync(0xffffffffu, jraw, 0);
+            if (jraw >= (unsigned long long)njobs_q) break;
+        }
+        const int job = (int)jraw;
+        const int strip = job - (job / nsp) * nsp;
+        const int sq = job / nsp;
+        const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);
+        const int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
+        const int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
+        if (strip >= f.nstrips) {                        // padding warp of a CTA job: keep the barriers company
+            const int nchp = ((y1 - y0) + 8 + RB - 1) / RB;
+            for (int c = 0; c < nchp; ++c) __syncthreads();
+            continue;
+        }
+        const int xs = strip * F2_OUTC - F2_HALO;
+        const int x = xs + 2 * lane;
+        // seam jobs store to the aliases as well (ghost columns / neighbour strips' ghost rows) and skip the ragged edge
+        const bool seam = strip == 0 || (strip + 1) * F2_OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
+        if (a.linked) {
+            if (lane == 0) {
+                if (y0 < GY + 2) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
+                if (y1 > a.ny - GY - 1) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
+            }
+            __syncwarp();
+        }
+        bool general = false;                            // jobs with a non-zero phi or theta anywhere belong to the general pass
+        bool live;                                       // some theta flag under the footprint is set -> look at theta itself
+        {
+            const int fby0 = max((y0 - 3 + GY) / FBY, 0);
+            const int bx0 = max((xs + GX) / FBX, 0), bx1 = min((xs + GX + 63) / FBX, a.nfbx - 1);
+            const int by1 = min((y1 + 2 + GY) / FBY, a.nfby - 1);
+            const int nbx = bx1 - bx0 + 1, nby = by1 - fby0 + 1;
+            uint32_t fl = 0;
+            for (int i = lane; i < nby * nbx; i += 32) fl |= __ldcg(&a.self.tflags[(fby0 + i / nbx) * a.nfbx + bx0 + i % nbx]);
+            live = __any_sync(0xffffffffu, fl != 0u);
+        }
+        const int nrows = (y1 - y0) + 8;                 // streamed phi^0 rows y0-4 .. y1+3
+        const int nch = (nrows + RB - 1) / RB;
+        int issued = 0;
+        {
+            const int box_x = xs - 4 + GX;
+            auto issue = [&](int c) {
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                float* dst = stages + st * STAGE_FLOATS;
+                mbar_expect_tx(&bars[st], 2 * RB * BW * 4);
+                const int yr = y0 - 4 + c * RB + GY;
+                tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
+                tma_load_2d(dst + BOX_FLOATS, map_t, box_x, yr - 1, &bars[st]);
+            };
+            issued = min(NST, nch);
+            if (lane == 0)
+                for (int c = 0; c < issued; ++c) issue(c);
+            F2Level L1, L2;
+            L1.clear(); L2.clear();
+            float2 t1_prev = f2(0.f);
+            const long long o4 = pidx<float>(pitch, x, y0 - 8);
+            float* pphi = phi_out + o4;
+            float* ptt = t_out + o4;
+            const unsigned int nstore = (lane >= 2 && lane <= 29) ? (unsigned int)(y1 - y0) : 0u;
+            for (int c = 0; c < nch; ++c) {
+                if (f.cta_jobs) __syncthreads();
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                if (general) {                           // abandoned job: drain what is in flight, keep the ring in step
+                    if (c < issued) mbar_wait(&bars[st], (gi / NST) & 1u);
+                    continue;
+                }
+                mbar_wait(&bars[st], (gi / NST) & 1u);
+                const float* sp = stages + st * STAGE_FLOATS + 2 * lane + 4;
+                const float* stt = sp + BOX_FLOATS;
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * BW]) | __float_as_uint(sp[rr * BW + 1]);
+                if (live) {                              // the flags are coarse (128 x 32 blocks): check the angles of these rows
+                    const int yr = y0 - 4 + c * RB + GY; // padded row of the chunk's first row
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr)
+                        if (yr + rr < a.ny + 2 * GY && x >= -GX && x + 1 < a.nx + GXR) {
+                            const float2 v = __ldg(reinterpret_cast<const float2*>(a.self.theta + (long long)(yr + rr) * pitch + (x + GX)));
+                            bits |= __float_as_uint(v.x) | __float_as_uint(v.y);
+                        }
+                }
+                if (__any_sync(0xffffffffu, bits != 0u)) { general = true; continue; }
+                const int yrel0 = c * RB - 8;
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const unsigned int yrel = (unsigned int)(yrel0 + rr);
+                    const float* row = stt + rr * BW;
+                    const float2 tn = *reinterpret_cast<const float2*>(row);
+                    const float2 t1 = f2_row_tonly(L1, C, tn, row[-1], row[2]);          // T^1 of row r-2
+                    const float tw2 = __shfl_up_sync(0xffffffffu, t1_prev.y, 1);
+                    const float te2 = __shfl_down_sync(0xffffffffu, t1_prev.x, 1);
+                    const float2 t2 = f2_row_tonly(L2, C, t1_prev, tw2, te2);            // T^2 of row r-4
+                    t1_prev = t1;
+                    if (yrel < nstore) {
+                        if (!seam) {
+                            *reinterpret_cast<float2*>(pphi) = f2(0.f);
+                            *reinterpret_cast<float2*>(ptt) = t2;
+                        } else {
+                            const int y = y0 + (int)yrel;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                if (x + k < a.nx) {
+                                    const float vt = k ? t2.y : t2.x;
+                                    if (y < GY || y >= a.ny - GY) {
+                                        fast_store_edge(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, 0.f);
+                                        fast_store_edge(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, vt);
+                                    } else {
+                                        pphi[k] = 0.f; ptt[k] = vt;
+                                        if (x + k < GXR) { pphi[k + a.nx] = 0.f; ptt[k + a.nx] = vt; }
+                                        if (x + k >= a.nx - GXR) { pphi[k - a.nx] = 0.f; ptt[k - a.nx] = vt; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    pphi += pitch; ptt += pitch;
+                }
+                __syncwarp();
+                if (c + NST < nch) {
+                    if (lane == 0) issue(c + NST);
+                    issued = c + NST + 1;
+                }
+            }
+            __syncwarp();
+            gchunk += (unsigned int)issued;
+        }
+        if (general && lane < 4) {                       // 4 row ranges per job
+            unsigned int pos = 0;
+            if (lane == 0) pos = atomicAdd(w.list_count, 4u);
+            pos = __shfl_sync(0x0000000fu, pos, 0);
+            w.list[pos + lane] = (sq * f.nstrips + strip) * 4 + lane;      // job id in the general pass's (unpadded) numbering
+        }
+    }
+}
+
 template <int JM, bool NOISE, bool ROT>
 __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
                                                                   const FastArgs f) {
@@ -282,12 +474,21 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
     const int njobs_q = nsp * f.nseg;
     for (;;) {
         unsigned long long jraw = 0;
+        int sub = -1;
         if (f.cta_jobs) {                                    // a CTA claims 8 adjacent strips of one segment
             __syncthreads();
             if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
             __syncthreads();
             if (s_job >= (unsigned long long)njobs_q) break;
             jraw = s_job + (unsigned long long)warp;
+        } else if (f.list) {                                 // general pass of a far/general launch pair: the work list
+            unsigned int idx = 0;
+            if (lane == 0) idx = atomicAdd(f.list_claim, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= *f.list_count) break;
+            jraw = (unsigned long long)f.list[idx];
+            sub = (int)(jraw & 3ull);                        // the far pass splits a job into 4 row ranges: short jobs keep
+            jraw >>= 2;                                      // the (latency-bound) general pass short
         } else {                                             // every warp claims its own job: no barrier anywhere
             if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
             jraw = __shfl_sync(0xffffffffu, jraw, 0);
@@ -297,8 +498,14 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         const int strip = job - (job / nsp) * nsp;
         const int sq = job / nsp;
         const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);     // the two torus-seam segments first
-        const int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
-        const int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
+        int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
+        int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
+        if (sub >= 0) {
+            const int q = (((y1 - y0 + 3) >> 2) + 3) & ~3;   // rows per sub-job, a multiple of 4
+            y0 += sub * q;
+            y1 = min(y0 + q, y1);
+            if (y0 >= y1) continue;
+        }
         const int xs = strip * F2_OUTC - F2_HALO;        // first pass-1 column of the warp
         const int x = xs + 2 * lane;                     // first cell of this lane
         const bool out_lane = lane >= 2 && lane <= 29;
