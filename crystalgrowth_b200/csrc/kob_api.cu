@@ -94,7 +94,19 @@ struct kob_ctx {
     double fast_frac_a = 0.9;
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
-    int fast2 = 0;                // two sub-steps per launch where kob_step(n >= 2) allows it (KOB_FAST2)
+    // Two sub-steps per launch pair (kob_fast2.cuh) where kob_step(n >= 2) allows it.  KOB_FAST2 = 0 never, 1 always,
+    // 2 (default) adaptive: the fraction of jobs with data-dependent work is read back asynchronously — the far pass's
+    // work-list length in pair mode, a live-job count of every 8th launch in single-step mode — and the single-step
+    // kernel is used while that fraction is high (the general pass of the pair runs at 8 warps/SM), with hysteresis.
+    // Results do not depend on the choice: both paths are bit-identical.
+    int fast2 = 2;
+    unsigned int* h_count = nullptr;   // pinned: work-list length of the last probed launch pair
+    cudaEvent_t ev_count = nullptr;
+    bool count_pending = false;
+    long long count_total = 1;
+    double general_frac = 0.0;
+    bool single_mode = false;          // adaptive policy: the field is dense, use the single-step kernel
+    uint64_t n_single = 0, n_paired = 0;
     int fast2_yj = 96, fast2_yj_b = 32, fast2_lock = 0, fast2_far = 1, fast2_far_cta = 1;
     int* worklist = nullptr;      // far/general launch pair: [count, claim, -, -, job ids ...]
     long long worklist_cap = 0;
@@ -240,7 +252,20 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
     f.job_base = c->job_expected;
+    // adaptive policy, single-step mode: every 8th launch counts its live jobs (read back asynchronously)
+    const bool probe = c->fast2 == 2 && c->single_mode && !c->count_pending && (c->launches & 7) == 0;
+    unsigned int* live_ctr = reinterpret_cast<unsigned int*>(c->base + c->L.off_ticket + 32);
+    if (probe) {
+        KOB_CUDA(c, cudaMemsetAsync(live_ctr, 0, sizeof(unsigned int), c->stream));
+        f.live_ctr = live_ctr;
+    }
     kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps, a, f);
+    if (probe) {
+        KOB_CUDA(c, cudaMemcpyAsync(c->h_count, live_ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
+        c->count_pending = true;
+        c->count_total = (long long)f.nstrips * f.nseg;
+    }
     c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * FAST_WARPS;   // every warp overshoots once
     return KOB_OK;
 }
@@ -326,6 +351,12 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         c->launches += 1;
         f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;
         kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+        if (c->fast2 == 2 && !c->count_pending && c->h_count) {          // density probe for the adaptive policy
+            KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+            KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
+            c->count_pending = true;
+            c->count_total = 4 * (long long)f.nstrips * f.nseg;
+        }
         return KOB_OK;
     }
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + F2_WARPS - 1) / F2_WARPS);
@@ -527,6 +558,9 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&c->ev_count, cudaEventDisableTiming)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaHostAlloc((void**)&c->h_count, 64, cudaHostAllocDefault)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    c->h_count[0] = 0u;
     if ((e = cudaMalloc((void**)&c->base, c->L.total)) != cudaSuccess)
         return bail(e == cudaErrorMemoryAllocation ? KOB_ERR_OOM : KOB_ERR_CUDA,
                     std::string("cudaMalloc(") + std::to_string(c->L.total) + "): " + cudaGetErrorString(e));
@@ -539,7 +573,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
-        if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::atoi(e_) ? 1 : 0;
+        if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
@@ -566,6 +600,8 @@ int kob_destroy(kob_ctx* c) {
     if (c->noise_field) cudaFree(c->noise_field);
     if (c->rgba) cudaFree(c->rgba);
     if (c->worklist) cudaFree(c->worklist);
+    if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_count) cudaEventDestroy(c->ev_count);
     if (c->base) cudaFree(c->base);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -611,9 +647,23 @@ int kob_get_params(const kob_ctx* c, kob_params* p) {
 int kob_step(kob_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
-    int64_t s = 0;
-    while (nsteps - s >= 2 && fast2_eligible(c)) { KOB_TRY(launch_two_steps_fast(c)); s += 2; }   // temporal blocking
-    for (; s < nsteps; ++s) KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
+    constexpr double FAST2_TO_SINGLE = 0.10, FAST2_TO_PAIR = 0.06;
+    for (int64_t s = 0; s < nsteps;) {
+        if (c->count_pending && cudaEventQuery(c->ev_count) == cudaSuccess) {       // a density probe has landed
+            c->count_pending = false;
+            c->general_frac = (double)c->h_count[0] / (double)c->count_total;
+            if (!c->single_mode && c->general_frac > FAST2_TO_SINGLE) c->single_mode = true;
+            else if (c->single_mode && c->general_frac < FAST2_TO_PAIR) c->single_mode = false;
+        }
+        const bool adaptive = c->fast2 == 2 && !c->linked;     // linked strips must all run the same launch sequence
+        if (nsteps - s >= 2 && fast2_eligible(c) && !(adaptive && c->single_mode)) {
+            KOB_TRY(launch_two_steps_fast(c));                  // temporal blocking: two sub-steps per launch pair
+            s += 2; c->n_paired += 2;
+        } else {
+            KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
+            s += 1; c->n_single += 1;
+        }
+    }
     return KOB_OK;
 }
 
@@ -718,6 +768,14 @@ int kob_render_rgba(kob_ctx* c, uint8_t* rgba) {
 
 int kob_sim_frame(const kob_ctx* c, int64_t* f) { if (!c || !f) return KOB_ERR_INVALID_ARG; *f = c->frames; return KOB_OK; }
 int kob_sim_time_ms(const kob_ctx* c, double* ms) { if (!c || !ms) return KOB_ERR_INVALID_ARG; *ms = c->sim_ms; return KOB_OK; }
+int kob_path_stats(const kob_ctx* c, uint64_t* single_steps, uint64_t* paired_steps, double* dense_fraction, int32_t* single_mode) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    if (single_steps) *single_steps = c->n_single;
+    if (paired_steps) *paired_steps = c->n_paired;
+    if (dense_fraction) *dense_fraction = c->general_frac;
+    if (single_mode) *single_mode = c->single_mode ? 1 : 0;
+    return KOB_OK;
+}
 int kob_launch_count(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->launches; return KOB_OK; }
 int kob_get_dims(const kob_ctx* c, int64_t* nx, int64_t* ny, int64_t* nyg, int64_t* y0) {
     if (!c) return KOB_ERR_INVALID_ARG;

@@ -65,6 +65,7 @@ struct FastArgs {
     const int* list;
     const unsigned int* list_count;
     unsigned int* list_claim;
+    unsigned int* live_ctr;        // single-step kernel, probe launches only: counts the jobs that see live theta flags
 };
 
 // Philox4x32-10 with the per-round keys (key + r * Weyl) precomputed on the host into the constant bank and the
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(32 * fast_warps<NP>(), NP == 2 ? 1 : 2) kob_st
             }
         }
         const bool live = livemask != 0u;
+        if (f.live_ctr && live && lane == 0 && strip < f.nstrips) atomicAdd(f.live_ctr, 1u);     // density probe (adaptive policy)
         // seam job: touches the first/last GXR columns or GY rows -> alias stores, ragged right edge
         const bool seam = strip == 0 || (strip + 1) * G::OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
 

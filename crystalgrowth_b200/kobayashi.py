@@ -253,6 +253,12 @@ class Kobayashi:
         self._ck(self._L.kob_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def path_stats(self) -> dict:
+        """Sub-steps done by the single-step kernel / by two-step launch pairs, last density probe, policy mode."""
+        a, b, fr, m = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_int32()
+        self._ck(self._L.kob_path_stats(self._h, C.byref(a), C.byref(b), C.byref(fr), C.byref(m)))
+        return {"single_steps": int(a.value), "paired_steps": int(b.value), "dense_fraction": float(fr.value), "single_mode": bool(m.value)}
+
     # ---- strips ----
     def ipc_export(self) -> bytes:
         h = KobIpcHandle()

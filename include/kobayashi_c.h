@@ -150,6 +150,9 @@ int kob_render_rgba(kob_ctx* ctx, uint8_t* rgba);
 int kob_sim_frame(const kob_ctx* ctx, int64_t* frames);      /* _simFrame, src/Kobayashi.cpp:238 */
 int kob_sim_time_ms(const kob_ctx* ctx, double* ms);         /* _simTime,  src/Kobayashi.cpp:237 */
 int kob_launch_count(const kob_ctx* ctx, uint64_t* launches);/* kernels launched by this context so far */
+/* Step-path bookkeeping (no reference counterpart): sub-steps done by the single-step kernel and by two-step launch
+ * pairs so far, the last density probe (fraction of jobs with data-dependent work) and the adaptive policy's mode. */
+int kob_path_stats(const kob_ctx* ctx, uint64_t* single_steps, uint64_t* paired_steps, double* dense_fraction, int32_t* single_mode);
 int kob_get_dims(const kob_ctx* ctx, int64_t* nx, int64_t* ny, int64_t* ny_global, int64_t* y0);
 const char* kob_last_error(const kob_ctx* ctx);              /* ctx may be NULL: last create error */
 const char* kob_strerror(int status);

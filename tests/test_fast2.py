@@ -1,0 +1,100 @@
+"""The two-step path (kob_fast2.cuh: far pass + general pass, two sub-steps per launch pair — SURVEY §8f rank 3) against
+the single-step kernel: BITWISE equality of phi, T and theta.  Everything that distinguishes the paths is covered:
+seam nuclei and ragged edges (wrapped noise keys, alias stores at ghost depth 4), odd step counts and mixed chunks
+(theta double buffer + in-place single steps), dense fields (general pass everywhere), every anisotropy variant,
+linked strips, the job-mode knobs, and the adaptive policy (KOB_FAST2=2), whose choices must not show in the results."""
+import numpy as np
+import pytest
+
+import bench
+from conftest import bit_equal
+
+pytestmark = pytest.mark.gpu
+
+SEAM_NUCLEI = [(0, 0), (350, 150), (699, 299), (100, 40), (520, 222)]
+
+
+def _run(cg, monkeypatch, fast2, nx, ny, nuclei, chunks, dense=False, env=(), **kw):
+    monkeypatch.setenv("KOB_FAST2", str(fast2))
+    for k, v in env:
+        monkeypatch.setenv(k, str(v))
+    g = cg.Kobayashi(nx, ny, 1e-4, kernel="fast", **kw)
+    g.clear()
+    for (x, y) in nuclei:
+        g.add_nucleus(x, y)
+    if dense:
+        phi, t = bench.dense_state(nx, ny, 0)
+        g.set_fields(phi, t, np.zeros((ny, nx), np.float32))
+    for n in chunks:
+        g.step(n)
+    out, launches = g.fields(), g.launch_count
+    g.close()
+    return out, launches
+
+
+CASES = {
+    "seam nuclei, noise, odd count": dict(nx=700, ny=300, nuclei=SEAM_NUCLEI, chunks=(151,), seed=11, noise_a=0.01),
+    "mixed chunks": dict(nx=150, ny=90, nuclei=[(0, 0), (75, 45), (149, 89), (30, 7), (120, 8)], chunks=(10, 3, 7, 1, 20, 19), seed=9, noise_a=0.01),
+    "dense j=6 noise": dict(nx=420, ny=200, nuclei=[], chunks=(40,), dense=True, seed=21, noise_a=0.01),
+    "dense j=4": dict(nx=420, ny=200, nuclei=[], chunks=(30,), dense=True, seed=21, noise_a=0.01, anisotropy=4.0),
+    "dense j=5 theta0": dict(nx=420, ny=200, nuclei=[], chunks=(30,), dense=True, seed=21, noise_a=0.01, anisotropy=5.0, theta0=0.3),
+    "dense j=5.5": dict(nx=420, ny=200, nuclei=[], chunks=(30,), dense=True, anisotropy=5.5),
+    "reference default 400": dict(nx=250, ny=250, nuclei=[(125, 125)], chunks=(400,)),
+    "tiny ragged": dict(nx=37, ny=23, nuclei=[(3, 3), (30, 20)], chunks=(30,), seed=2, noise_a=0.01),
+    "wide far field": dict(nx=3000, ny=700, nuclei=[(1500, 350), (10, 690), (2990, 5)], chunks=(120,), seed=4, noise_a=0.01),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_two_step_path_is_bit_identical_to_single_steps(cg, monkeypatch, name):
+    kw = CASES[name]
+    (a, la), (b, lb) = _run(cg, monkeypatch, 0, **kw), _run(cg, monkeypatch, 1, **kw)
+    assert all(bit_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("env", [(("KOB_FAST2_FAR", 0),), (("KOB_FAST2_FAR", 0), ("KOB_FAST2_LOCK", 2)), (("KOB_FAST2_FAR_CTA", 0),),
+                                 (("KOB_FAST2_YJ", 20),), (("KOB_FAST2_YJ", 256),)])
+def test_two_step_job_modes_are_bit_neutral(cg, monkeypatch, env):
+    kw = CASES["seam nuclei, noise, odd count"]
+    (a, _), (b, _) = _run(cg, monkeypatch, 0, **kw), _run(cg, monkeypatch, 1, env=env, **kw)
+    assert all(bit_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name", ["seam nuclei, noise, odd count", "dense j=6 noise"])
+def test_adaptive_policy_does_not_show_in_the_results(cg, monkeypatch, name):
+    """KOB_FAST2=2 (the default) switches between the paths on an asynchronously read density probe: timing dependent,
+    therefore required to be invisible."""
+    kw = dict(CASES[name])
+    kw["chunks"] = (10,) * 12
+    (a, _), (b, _) = _run(cg, monkeypatch, 0, **kw), _run(cg, monkeypatch, 2, **kw)
+    assert all(bit_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("nstrips,nyg", [(2, 64), (3, 70)])
+def test_two_step_linked_strips(cg, monkeypatch, nstrips, nyg):
+    from crystalgrowth_b200.strips import partition
+    nx, steps = 200, 40
+    nuclei = [(3, 0), (100, nyg // 2), (199, nyg - 1), (20, nyg // nstrips), (70, nyg // nstrips - 1)]
+    outs = []
+    for fast2 in (0, 1):
+        monkeypatch.setenv("KOB_FAST2", str(fast2))
+        strips = [cg.Kobayashi(nx, ny, 1e-4, kernel="fast", ny_global=nyg, y0=y0, seed=5, noise_a=0.01) for (y0, ny) in partition(nyg, nstrips)]
+        for i, s in enumerate(strips):
+            s.link_local(strips[(i - 1) % nstrips], strips[(i + 1) % nstrips])
+            s.clear()
+        for (x, y) in nuclei:
+            for s in strips:
+                s.add_nucleus(x, y)
+        for s in strips:
+            s.sync()
+        for s in strips:
+            s.halo_refresh()
+        for s in strips:
+            s.sync()
+        for _ in range(steps // 2):
+            for s in strips:
+                s.step(2)
+        outs.append([np.concatenate(parts, axis=0) for parts in zip(*[s.fields() for s in strips])])
+        for s in strips:
+            s.close()
+    assert all(bit_equal(x, y) for x, y in zip(*outs))

@@ -405,6 +405,7 @@ def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, np_):
     into phi == 0 territory; noise is on."""
     def run(noskip):
         monkeypatch.setenv("KOB_FAST_NOSKIP", str(noskip))
+        monkeypatch.setenv("KOB_FAST2", "0")             # the single-step kernel's shortcut is what is under test
         monkeypatch.setenv("KOB_FAST_CTA", str(cta))
         monkeypatch.setenv("KOB_FAST_NP", str(np_))
         monkeypatch.setenv("KOB_FAST_YJ", "32")
