@@ -252,10 +252,11 @@ __device__ __forceinline__ void f2_row(F2Level& S, const F2Const& C, const KPara
 // The two-step kernel needs ~230 registers (two sets of windows + the data-dependent block), i.e. 8 warps per SM — too
 // few to keep HBM busy on the far-field rows, which need almost none of that state.  So a launch pair is used:
 //   1. kob_far2 (this kernel, ~48 registers, 24 warps per SM) visits EVERY job.  Interior jobs whose theta flags are
-//      clear are streamed (seam jobs too, with alias stores); as long as every phi^0 chunk seen so far is all +0 the rows only diffuse T (twice, level 2
-//      from level 1's rows in registers) — the same instructions as kob_step_fast2's shortcut, bit for bit.  A job that
-//      is on a seam, has live theta, or meets a non-zero phi chunk is appended to the work list instead (rows already
-//      stored are valid — they depend only on rows seen to be zero — and will simply be stored again).
+//      clear are streamed (seam jobs too, with alias stores); every row goes through two T-diffusion sub-steps (level 2
+//      from level 1's rows in registers) — the same instructions as kob_step_fast2's shortcut, bit for bit — and is
+//      STORED where the 12 rows up to it are all +0 in phi (and, under a set theta flag, 0 in theta).  A job is cut
+//      into 4 row ranges; ranges with unstored rows are appended to the work list (rows both passes store get the same
+//      bits twice).
 //   2. kob_step_fast2 then processes the work list.
 struct Far2Args {
     int* list;                  // job ids for the general pass
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             }
             __syncwarp();
         }
-        bool general = false;                            // jobs with a non-zero phi or theta anywhere belong to the general pass
+        uint32_t need_out = 0u;                          // row ranges of this job that the general pass has to do
         bool live;                                       // some theta flag under the footprint is set -> look at theta itself
         {
             const int fby0 = max((y0 - 3 + GY) / FBY, 0);
@@ -362,15 +363,15 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             const long long o4 = pidx<float>(pitch, x, y0 - 8);
             float* pphi = phi_out + o4;
             float* ptt = t_out + o4;
-            const unsigned int nstore = (lane >= 2 && lane <= 29) ? (unsigned int)(y1 - y0) : 0u;
+            const unsigned int nvalid = (unsigned int)(y1 - y0);
+            const unsigned int nstore = (lane >= 2 && lane <= 29) ? nvalid : 0u;
+            const int q = ((((int)nvalid + 3) >> 2) + 3) & ~3;       // rows per row range (kob_step_fast2 decodes the same way)
+            bool z1 = false, z2 = false;                             // the previous two chunks were all zero
+            uint32_t need = 0u;                                      // row ranges (4 per job) that need the general pass
             for (int c = 0; c < nch; ++c) {
                 if (f.cta_jobs) __syncthreads();
                 const unsigned int gi = gchunk + (unsigned int)c;
                 const int st = gi % NST;
-                if (general) {                           // abandoned job: drain what is in flight, keep the ring in step
-                    if (c < issued) mbar_wait(&bars[st], (gi / NST) & 1u);
-                    continue;
-                }
                 mbar_wait(&bars[st], (gi / NST) & 1u);
                 const float* sp = stages + st * STAGE_FLOATS + 2 * lane + 4;
                 const float* stt = sp + BOX_FLOATS;
@@ -386,8 +387,18 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                             bits |= __float_as_uint(v.x) | __float_as_uint(v.y);
                         }
                 }
-                if (__any_sync(0xffffffffu, bits != 0u)) { general = true; continue; }
+                // Rows are always pushed through the T windows (they only see T^0, which is real data); a row's result is
+                // STORED only if this chunk and the two before it are all zero — then phi^0 == +0 (and theta == 0) over the
+                // 9 rows the two composed sub-steps look at, and T^1 in level 2's window carries no missing K (phi^1 - phi^0)
+                // term.  Row ranges with unstored rows go to the general pass.
+                const bool z0 = !__any_sync(0xffffffffu, bits != 0u);
+                const bool ok = z0 && z1 && z2;
+                z2 = z1; z1 = z0;
                 const int yrel0 = c * RB - 8;
+                if (!ok) {
+                    const int ra = max(yrel0, 0), rb = min(yrel0 + RB - 1, (int)nvalid - 1);
+                    if (ra <= rb) need |= (1u << (ra / q)) | (1u << (rb / q));
+                }
 #pragma unroll
                 for (int rr = 0; rr < RB; ++rr) {
                     const unsigned int yrel = (unsigned int)(yrel0 + rr);
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                     const float te2 = __shfl_down_sync(0xffffffffu, t1_prev.x, 1);
                     const float2 t2 = f2_row_tonly(L2, C, t1_prev, tw2, te2);            // T^2 of row r-4
                     t1_prev = t1;
-                    if (yrel < nstore) {
+                    if (ok && yrel < nstore) {
                         if (!seam) {
                             *reinterpret_cast<float2*>(pphi) = f2(0.f);
                             *reinterpret_cast<float2*>(ptt) = t2;
@@ -430,12 +441,14 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             }
             __syncwarp();
             gchunk += (unsigned int)issued;
+            need_out = need;
         }
-        if (general && lane < 4) {                       // 4 row ranges per job
+        if (need_out) {                                  // append the row ranges (of 4 per job) that were not fully stored
             unsigned int pos = 0;
-            if (lane == 0) pos = atomicAdd(w.list_count, 4u);
-            pos = __shfl_sync(0x0000000fu, pos, 0);
-            w.list[pos + lane] = (sq * f.nstrips + strip) * 4 + lane;      // job id in the general pass's (unpadded) numbering
+            if (lane == 0) pos = atomicAdd(w.list_count, (unsigned int)__popc(need_out));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (lane < 4 && ((need_out >> lane) & 1u))
+                w.list[pos + __popc(need_out & ((1u << lane) - 1u))] = (sq * f.nstrips + strip) * 4 + lane;   // unpadded job numbering
         }
     }
 }
