@@ -10,12 +10,15 @@ Workload (config.workload): BASELINE.json configs[2], "16384^2 multi-seed with P
 16384 x (16384*N) torus, 64*N nuclei, ring-linked through CUDA-IPC peer stores issued by the step kernel.
 
 One "step" = one call of the reference's plugin entry point Kobayashi::iUpdate (src/Kobayashi.cpp:227-239)
-= `--substeps` (10) explicit-Euler sub-steps = 10 launches of the fused kernel.
+= `--substeps` (10) explicit-Euler sub-steps = 10 launches of the fused single-step kernel, or 5 two-step launch pairs
+(far pass + general pass; the library picks the path, results are bit-identical — kob_path_stats says which ran).
 
   value  Gcell-updates/s with the state resident in HBM, CUDA-event timed on the library's stream, max over ranks
   e2e    same metric through the host-buffer plugin call: every step copies phi, T, theta from pinned host
          memory to the device (kob_set_fields), runs the sub-steps, and reads phi and T back (kob_get_fields)
-  roofline  16 B per cell-update (phi and T read once + written once, FP32) / avg launch duration
+  roofline  16 B per cell-update (phi and T read once + written once, FP32) x cell-updates per launch /
+         avg launch duration (a "launch" is one sub-step, or one two-step PAIR); with pairs the measured DRAM traffic
+         (dram_achieved / dram_frac) is reported next to the algorithmic figure, which can exceed the copy peak
   cpu_baseline  the reference's own CPU loop (oracle/_ref when built, else the oracle port), 1 thread (the
          reference is single threaded), timed on this box on a bounded sample
 `--impl reference` times only that CPU loop (the reference arm).

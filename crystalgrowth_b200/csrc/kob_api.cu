@@ -327,7 +327,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         // far/general launch pair: the light far pass visits every job and leaves the rest on the work list
         if (c->worklist_cap < njobs) {
             if (c->worklist) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->worklist); c->worklist = nullptr; }
-            KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(4 * njobs + 4) * sizeof(int)));
+            KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(F2_RANGES * njobs + 4) * sizeof(int)));
             c->worklist_cap = njobs;
         }
         unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim
@@ -355,7 +355,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
             KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
             KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
             c->count_pending = true;
-            c->count_total = 4 * (long long)f.nstrips * f.nseg;
+            c->count_total = (long long)F2_RANGES * f.nstrips * f.nseg;
         }
         return KOB_OK;
     }

@@ -33,6 +33,11 @@ constexpr int F2_HALO = 4;      // pass-1 columns left of the first output colum
 #endif
 constexpr int F2_WARPS = KOB_F2_WARPS;
 constexpr int F2_NST = KOB_F2_NST;   // TMA stages per warp (one CTA per SM: a deeper ring than the single-step kernel's)
+#ifndef KOB_F2_RANGES
+#define KOB_F2_RANGES 4
+#endif
+constexpr int F2_RANGES = KOB_F2_RANGES;    // row ranges per job handed to the general pass (power of two; 2 and 8 measured slower)
+__host__ __device__ constexpr int f2_range_rows(int rows) { return (((rows + F2_RANGES - 1) / F2_RANGES) + 3) & ~3; }
 constexpr int F2_BW = 72;       // TMA box width: columns xs-4 .. xs+67 (the box must start on a 16-byte boundary)
 constexpr int F2_BOX_FLOATS = (FAST_RB * F2_BW + 31) / 32 * 32;
 constexpr int F2_STAGE_FLOATS = 2 * F2_BOX_FLOATS;
@@ -255,7 +260,7 @@ __device__ __forceinline__ void f2_row(F2Level& S, const F2Const& C, const KPara
 //      clear are streamed (seam jobs too, with alias stores); every row goes through two T-diffusion sub-steps (level 2
 //      from level 1's rows in registers) — the same instructions as kob_step_fast2's shortcut, bit for bit — and is
 //      STORED where the 12 rows up to it are all +0 in phi (and, under a set theta flag, 0 in theta).  A job is cut
-//      into 4 row ranges; ranges with unstored rows are appended to the work list (rows both passes store get the same
+//      into F2_RANGES row ranges; ranges with unstored rows are appended to the work list (rows both passes store get the same
 //      bits twice).
 //   2. kob_step_fast2 then processes the work list.
 struct Far2Args {
@@ -365,9 +370,9 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             float* ptt = t_out + o4;
             const unsigned int nvalid = (unsigned int)(y1 - y0);
             const unsigned int nstore = (lane >= 2 && lane <= 29) ? nvalid : 0u;
-            const int q = ((((int)nvalid + 3) >> 2) + 3) & ~3;       // rows per row range (kob_step_fast2 decodes the same way)
+            const int q = f2_range_rows((int)nvalid);                // rows per row range (kob_step_fast2 decodes the same way)
             bool z1 = false, z2 = false;                             // the previous two chunks were all zero
-            uint32_t need = 0u;                                      // row ranges (4 per job) that need the general pass
+            uint32_t need = 0u;                                      // row ranges (F2_RANGES per job) that need the general pass
             for (int c = 0; c < nch; ++c) {
                 if (f.cta_jobs) __syncthreads();
                 const unsigned int gi = gchunk + (unsigned int)c;
@@ -443,12 +448,12 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             gchunk += (unsigned int)issued;
             need_out = need;
         }
-        if (need_out) {                                  // append the row ranges (of 4 per job) that were not fully stored
+        if (need_out) {                                  // append the row ranges that were not fully stored
             unsigned int pos = 0;
             if (lane == 0) pos = atomicAdd(w.list_count, (unsigned int)__popc(need_out));
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (lane < 4 && ((need_out >> lane) & 1u))
-                w.list[pos + __popc(need_out & ((1u << lane) - 1u))] = (sq * f.nstrips + strip) * 4 + lane;   // unpadded job numbering
+            if (lane < F2_RANGES && ((need_out >> lane) & 1u))
+                w.list[pos + __popc(need_out & ((1u << lane) - 1u))] = (sq * f.nstrips + strip) * F2_RANGES + lane;   // unpadded job numbering
         }
     }
 }
@@ -500,8 +505,8 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
             idx = __shfl_sync(0xffffffffu, idx, 0);
             if (idx >= *f.list_count) break;
             jraw = (unsigned long long)f.list[idx];
-            sub = (int)(jraw & 3ull);                        // the far pass splits a job into 4 row ranges: short jobs keep
-            jraw >>= 2;                                      // the (latency-bound) general pass short
+            sub = (int)(jraw & (unsigned long long)(F2_RANGES - 1));   // the far pass cuts a job into F2_RANGES row ranges:
+            jraw /= F2_RANGES;                               // short jobs keep the (latency-bound) general pass short
         } else {                                             // every warp claims its own job: no barrier anywhere
             if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
             jraw = __shfl_sync(0xffffffffu, jraw, 0);
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
         int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
         if (sub >= 0) {
-            const int q = (((y1 - y0 + 3) >> 2) + 3) & ~3;   // rows per sub-job, a multiple of 4
+            const int q = f2_range_rows(y1 - y0);            // rows per sub-job, a multiple of 4
             y0 += sub * q;
             y1 = min(y0 + q, y1);
             if (y0 >= y1) continue;

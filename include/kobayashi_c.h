@@ -120,8 +120,10 @@ int kob_get_params(const kob_ctx* ctx, kob_params* p);
 
 /* ---- the hot path --------------------------------------------------------------- */
 
-/* nsteps x { _computeGradientLaplacian(); _evolution(); } (src/Kobayashi.cpp:230-234), one fused
- * kernel launch per step, asynchronous. */
+/* nsteps x { _computeGradientLaplacian(); _evolution(); } (src/Kobayashi.cpp:230-234), asynchronous.
+ * One fused kernel launch per sub-step; with the FAST kernel, pairs of sub-steps may instead run as one
+ * two-step launch pair (phi and T cross HBM once per two sub-steps).  The choice (environment KOB_FAST2 =
+ * 0 never | 1 always | 2 adaptive, the default) never shows in the results: both paths are bit-identical. */
 int kob_step(kob_ctx* ctx, int64_t nsteps);
 /* Kobayashi::iUpdate (src/Kobayashi.cpp:227-239): 10 sub-steps, then _simFrame++ and
  * _simTime += elapsed ms. */
