@@ -647,7 +647,10 @@ int kob_get_params(const kob_ctx* c, kob_params* p) {
 int kob_step(kob_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
-    constexpr double FAST2_TO_SINGLE = 0.10, FAST2_TO_PAIR = 0.06;
+    // Break-even of the two paths (B200, 16384^2): a pair costs ~0.73 ms + 20 ms x g (general pass at 8 warps/SM), two single
+    // steps ~2 x (0.69 + 1.65 g) ms, g = fraction of row ranges with crystal  ->  g ~ 0.04.  The single-step probe counts
+    // jobs under a set theta flag (128 x 32 blocks), which over-estimates g: that is the hysteresis.
+    constexpr double FAST2_TO_SINGLE = 0.04, FAST2_TO_PAIR = 0.04;
     for (int64_t s = 0; s < nsteps;) {
         if (c->count_pending && cudaEventQuery(c->ev_count) == cudaSuccess) {       // a density probe has landed
             c->count_pending = false;
