@@ -601,12 +601,22 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                 const float* sp = stages + st * STAGE_FLOATS + 2 * lane + 4;       // this lane's own phi cells
                 const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
                 const int yrel0 = c * RB - 8;                                      // (r - 4) - y0 for rr = 0
-                if (!GEN) {
-                    // far field: phi^0 == +0 on the 64 own columns of this chunk and of the two chunks before it -> both
-                    // levels only diffuse T (level 2 from level 1's rows in registers); bit-identical to the full path
+                if (!GEN || !seam) {
+                    // far field: phi^0 == +0 (and, where theta flags are live, theta^0 == 0) on the 64 own columns of this
+                    // chunk and of the two chunks before it -> both levels only diffuse T (level 2 from level 1's rows in
+                    // registers); bit-identical to the full path.  Seam jobs (alias stores) always take the full path.
                     uint32_t bits = 0u;
 #pragma unroll
                     for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * BW]) | __float_as_uint(sp[rr * BW + 1]);
+                    if (GEN) {
+                        const int yr = y0 - 4 + c * RB + GY;                         // padded row of the chunk's first row
+#pragma unroll
+                        for (int rr = 0; rr < RB; ++rr)
+                            if (yr + rr < a.ny + 2 * GY) {
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(a.self.theta + (long long)(yr + rr) * pitch + (x + GX)));
+                                bits |= __float_as_uint(v.x) | __float_as_uint(v.y);
+                            }
+                    }
                     const bool curz = !__any_sync(0xffffffffu, bits != 0u);
                     const bool skip = curz && pz1 && pz2 && !f.no_skip;
                     pz2 = pz1; pz1 = curz;
@@ -626,6 +636,17 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                                 *reinterpret_cast<float2*>(ptt) = t2;
                             }
                             pphi += pitch; ptt += pitch; pthn += pitch; pth0 += pitch;
+                        }
+                        if (GEN) {
+                            // the angle pipelines skipped 4 rows that hold theta == 0; re-prime them for the next chunk's
+                            // first row r': theta^0(r'-1) = 0 (this chunk), theta^0(r') is loaded now
+                            e1[0] = e1[1] = e2[0] = e2[1] = 0.f;
+                            thp0[0] = thp0[1] = 0.f;
+                            thp1[0] = thp1[1] = 0.f;
+                            if ((unsigned int)(yrel0 + RB) + 7u <= nvalid + 5u) {                // row r' <= y1 + 2
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(pth0 - pitch));
+                                thp1[0] = v.x; thp1[1] = v.y;
+                            }
                         }
                         __syncwarp();
                         if (lane == 0 && c + NST < nch) issue(c + NST);
