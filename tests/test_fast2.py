@@ -98,3 +98,19 @@ def test_two_step_linked_strips(cg, monkeypatch, nstrips, nyg):
         for s in strips:
             s.close()
     assert all(bit_equal(x, y) for x, y in zip(*outs))
+
+
+def test_two_step_path_randomised(cg, monkeypatch):
+    """Seeded random grids, nuclei (seams included), anisotropy variants, noise and step chunking: pairs == single steps."""
+    rng = np.random.default_rng(20260101)
+    for case in range(14):
+        nx, ny = int(rng.integers(8, 330)), int(rng.integers(8, 230))
+        nuclei = [(int(rng.integers(0, nx)), int(rng.integers(0, ny))) for _ in range(int(rng.integers(1, 6)))]
+        if case % 3 == 0:
+            nuclei += [(0, 0), (nx - 1, ny - 1)]
+        j, theta0 = [(6.0, 0.0), (4.0, 0.0), (5.0, 0.25), (5.5, 0.0), (3.0, 0.0)][case % 5]
+        chunks = tuple(int(c) for c in rng.integers(1, 40, size=int(rng.integers(1, 5))))
+        kw = dict(nx=nx, ny=ny, nuclei=nuclei, chunks=chunks, seed=int(rng.integers(0, 2**31)),
+                  noise_a=float(rng.choice([0.0, 0.01, 0.05])), anisotropy=j, theta0=theta0)
+        (a, _), (b, _) = _run(cg, monkeypatch, 0, **kw), _run(cg, monkeypatch, 1, **kw)
+        assert all(bit_equal(x, y) for x, y in zip(a, b)), f"case {case}: {kw}"
