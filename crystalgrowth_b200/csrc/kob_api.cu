@@ -89,7 +89,7 @@ struct kob_ctx {
     bool linked = false;
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
-    FastMaps maps{}, maps2{};
+    FastMaps maps{}, maps2{}, maps_far{};   // single-step boxes; two-step boxes (72 wide); far pass: phi 64 wide + T 72 wide
     int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
     double fast_frac_a = 0.9;
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
@@ -219,6 +219,14 @@ int build_fast_maps(kob_ctx* c) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     }
+    const cuuint32_t box3[2] = {(cuuint32_t)FAR2_PBW, (cuuint32_t)FAST_RB};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = enc(&c->maps_far.phi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box3, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        c->maps_far.t[i] = c->maps2.t[i];
+    }
     return KOB_OK;
 }
 
@@ -346,7 +354,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         const long long fjobs = (long long)(ff.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
         ff.job_base = c->job_expected;
         const int fgrid = (int)std::min<long long>((long long)nsm * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
-        kob_far2<<<fgrid, FAR2_WARPS * 32, far_smem, c->stream>>>(c->maps2, a, ff, w);
+        kob_far2<<<fgrid, FAR2_WARPS * 32, far_smem, c->stream>>>(c->maps_far, a, ff, w);
         c->job_expected += (unsigned long long)fjobs + (unsigned long long)fgrid * FAR2_WARPS;
         c->launches += 1;
         f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;

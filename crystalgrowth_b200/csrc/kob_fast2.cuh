@@ -270,12 +270,15 @@ struct Far2Args {
 
 constexpr int FAR2_WARPS = 8;
 constexpr int FAR2_NST = 4;
-constexpr int FAR2_WARP_BYTES = FAR2_NST * F2_STAGE_FLOATS * 4;
+constexpr int FAR2_PBW = 64;    // phi box: exactly the 64 own columns (only looked at: are they all +0?)
+constexpr int FAR2_PBOX_FLOATS = FAST_RB * FAR2_PBW;                       // 1024 B, a multiple of 128
+constexpr int FAR2_STAGE_FLOATS = FAR2_PBOX_FLOATS + F2_BOX_FLOATS;       // phi box (64 wide) + T box (72 wide)
+constexpr int FAR2_WARP_BYTES = FAR2_NST * FAR2_STAGE_FLOATS * 4;
 
 __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
                                                               const FastArgs f, const Far2Args w) {
     constexpr int BW = F2_BW, RB = FAST_RB, NST = FAR2_NST;
-    constexpr int STAGE_FLOATS = F2_STAGE_FLOATS, BOX_FLOATS = F2_BOX_FLOATS;
+    constexpr int STAGE_FLOATS = FAR2_STAGE_FLOATS, PBW = FAR2_PBW, PBOX_FLOATS = FAR2_PBOX_FLOATS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float* stages = reinterpret_cast<float*>(smem_raw) + (size_t)warp * NST * STAGE_FLOATS;
@@ -354,10 +357,10 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                 const unsigned int gi = gchunk + (unsigned int)c;
                 const int st = gi % NST;
                 float* dst = stages + st * STAGE_FLOATS;
-                mbar_expect_tx(&bars[st], 2 * RB * BW * 4);
+                mbar_expect_tx(&bars[st], RB * (PBW + BW) * 4);
                 const int yr = y0 - 4 + c * RB + GY;
-                tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
-                tma_load_2d(dst + BOX_FLOATS, map_t, box_x, yr - 1, &bars[st]);
+                tma_load_2d(dst, map_phi, box_x + 4, yr, &bars[st]);                 // phi: columns xs .. xs+63
+                tma_load_2d(dst + PBOX_FLOATS, map_t, box_x, yr - 1, &bars[st]);     // T:   columns xs-4 .. xs+67
             };
             issued = min(NST, nch);
             if (lane == 0)
@@ -378,11 +381,11 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                 const unsigned int gi = gchunk + (unsigned int)c;
                 const int st = gi % NST;
                 mbar_wait(&bars[st], (gi / NST) & 1u);
-                const float* sp = stages + st * STAGE_FLOATS + 2 * lane + 4;
-                const float* stt = sp + BOX_FLOATS;
+                const float* sp = stages + st * STAGE_FLOATS + 2 * lane;           // this lane's own phi cells
+                const float* stt = stages + st * STAGE_FLOATS + PBOX_FLOATS + 2 * lane + 4;   // ... and T cells (one row behind)
                 uint32_t bits = 0u;
 #pragma unroll
-                for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * BW]) | __float_as_uint(sp[rr * BW + 1]);
+                for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * PBW]) | __float_as_uint(sp[rr * PBW + 1]);
                 if (live) {                              // the flags are coarse (128 x 32 blocks): check the angles of these rows
                     const int yr = y0 - 4 + c * RB + GY; // padded row of the chunk's first row
 #pragma unroll
