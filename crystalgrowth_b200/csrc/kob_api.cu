@@ -91,6 +91,7 @@ struct kob_ctx {
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
     FastMaps maps{}, maps2{}, maps_far{};   // single-step boxes; two-step boxes (72 wide); far pass: phi 64 wide + T 72 wide
     int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
+    bool fast_yj_env = false, fast2_yj_env = false;   // job heights given explicitly: no automatic shortening
     double fast_frac_a = 0.9;
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
     int fast_no_skip = 0;
@@ -232,6 +233,14 @@ int build_fast_maps(kob_ctx* c) {
 
 
 
+// Rows per job: the configured height, halved while the job queue is shorter than the persistent grid (not when the
+// height was set explicitly through the environment).
+int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps) {
+    if (fixed) return yj;
+    while (yj > 4 && (long long)nstrips * ((ny + yj - 1) / yj) < warps) yj /= 2;
+    return std::max(4, yj / 4 * 4);
+}
+
 template <int NP, int JM, bool NOISE, bool ROT>
 int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     auto kern = kob_step_fast<NP, JM, NOISE, ROT>;
@@ -247,14 +256,16 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     int nsm = 0;
     KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     f.nstrips = (int)((c->nx + FastGeom<NP>::OUTC - 1) / FastGeom<NP>::OUTC);
-    // guided job heights: fast_yj rows for the first fast_frac_a of the strip, fast_yj_b rows for the rest
-    f.yj = c->fast_yj;
-    f.yj_b = std::min(c->fast_yj_b, c->fast_yj);
+    // guided job heights: fast_yj rows for the first fast_frac_a of the strip, fast_yj_b rows for the rest; on small
+    // grids the jobs are made shorter until every warp of the persistent grid has one (a warp marches its job serially:
+    // 250^2 with 64-row jobs is 20 warps at work, 62 us per launch; with 4-row jobs 12 us).  Bit-neutral.
+    f.yj = auto_job_rows(c->fast_yj, c->fast_yj_env, f.nstrips, c->ny, (long long)nsm * cps * FAST_WARPS);
+    f.yj_b = std::min(c->fast_yj_b, f.yj);
     f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
     if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
     const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
     f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
-    f.cta_jobs = c->fast_cta_jobs;
+    f.cta_jobs = f.nstrips < FAST_WARPS ? 0 : c->fast_cta_jobs;   // narrow grids: a CTA job would be mostly padding warps
     f.no_skip = c->fast_no_skip;
     f.nstrips_p = (f.nstrips + FAST_WARPS - 1) / FAST_WARPS * FAST_WARPS;
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
@@ -321,8 +332,8 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     int nsm = 0;
     KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     f.nstrips = (int)((c->nx + F2_OUTC - 1) / F2_OUTC);
-    f.yj = c->fast2_yj;
-    f.yj_b = std::min(c->fast2_yj_b, c->fast2_yj);
+    f.yj = auto_job_rows(c->fast2_yj, c->fast2_yj_env, f.nstrips, c->ny, (long long)nsm * 3 * FAR2_WARPS);
+    f.yj_b = std::min(c->fast2_yj_b, f.yj);
     f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
     if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
     const long long rest = std::max<long long>(0, c->ny - (long long)f.nseg_a * f.yj);
@@ -350,7 +361,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         }
         Far2Args w{c->worklist + 4, counters};
         FastArgs ff = f;
-        ff.cta_jobs = c->fast2_far_cta;
+        ff.cta_jobs = f.nstrips < FAR2_WARPS ? 0 : c->fast2_far_cta;      // narrow grids: a CTA job would be mostly padding
         const long long fjobs = (long long)(ff.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
         ff.job_base = c->job_expected;
         const int fgrid = (int)std::min<long long>((long long)nsm * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
@@ -578,11 +589,11 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     if (c->kernel == KOB_KERNEL_FAST) {
         // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
         if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
-        if (const char* e_ = std::getenv("KOB_FAST_YJ")) c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST_YJ")) { c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_)); c->fast_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::min(2, std::max(0, std::atoi(e_)));
-        if (const char* e_ = std::getenv("KOB_FAST2_YJ")) c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_YJ")) { c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_)); c->fast2_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;
