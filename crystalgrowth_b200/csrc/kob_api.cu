@@ -233,12 +233,19 @@ int build_fast_maps(kob_ctx* c) {
 
 
 
-// Rows per job: the configured height, halved while the job queue is shorter than the persistent grid (not when the
-// height was set explicitly through the environment).
-int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps) {
+// Rows per job: the configured height or a shorter one (halvings down to 4) — whichever minimises the serial work of the
+// busiest warp, rounds x (rows + warm-up rows).  On big grids that is the configured height; on small ones the jobs shrink
+// until every warp of the persistent grid has one.  Not applied when the height was set explicitly (environment).
+int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps, int warm) {
     if (fixed) return yj;
-    while (yj > 4 && (long long)nstrips * ((ny + yj - 1) / yj) < warps) yj /= 2;
-    return std::max(4, yj / 4 * 4);
+    int best = yj;
+    long long best_cost = -1;
+    for (int h = yj; h >= 4; h /= 2) {
+        const long long jobs = (long long)nstrips * ((ny + h - 1) / h);
+        const long long cost = ((jobs + warps - 1) / warps) * (h + warm);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = h; }
+    }
+    return std::max(4, best / 4 * 4);
 }
 
 template <int NP, int JM, bool NOISE, bool ROT>
@@ -259,7 +266,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     // guided job heights: fast_yj rows for the first fast_frac_a of the strip, fast_yj_b rows for the rest; on small
     // grids the jobs are made shorter until every warp of the persistent grid has one (a warp marches its job serially:
     // 250^2 with 64-row jobs is 20 warps at work, 62 us per launch; with 4-row jobs 12 us).  Bit-neutral.
-    f.yj = auto_job_rows(c->fast_yj, c->fast_yj_env, f.nstrips, c->ny, (long long)nsm * cps * FAST_WARPS);
+    f.yj = auto_job_rows(c->fast_yj, c->fast_yj_env, f.nstrips, c->ny, (long long)nsm * cps * FAST_WARPS, 4);
     f.yj_b = std::min(c->fast_yj_b, f.yj);
     f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
     if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
@@ -332,7 +339,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     int nsm = 0;
     KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
     f.nstrips = (int)((c->nx + F2_OUTC - 1) / F2_OUTC);
-    f.yj = auto_job_rows(c->fast2_yj, c->fast2_yj_env, f.nstrips, c->ny, (long long)nsm * 3 * FAR2_WARPS);
+    f.yj = auto_job_rows(c->fast2_yj, c->fast2_yj_env, f.nstrips, c->ny, (long long)nsm * 3 * FAR2_WARPS, 8);
     f.yj_b = std::min(c->fast2_yj_b, f.yj);
     f.nseg_a = (int)(((double)c->ny * c->fast_frac_a) / f.yj);
     if ((long long)f.nseg_a * f.yj >= c->ny || f.yj_b == f.yj) f.nseg_a = (int)((c->ny + f.yj - 1) / f.yj);
