@@ -141,6 +141,14 @@ public:
     int64_t simFrame() const { int64_t f = 0; ck(kob_sim_frame(ctx_, &f), "kob_sim_frame"); return f; }
     double simTimeMs() const { double ms = 0; ck(kob_sim_time_ms(ctx_, &ms), "kob_sim_time_ms"); return ms; }
     uint64_t launchCount() const { uint64_t n = 0; ck(kob_launch_count(ctx_, &n), "kob_launch_count"); return n; }
+    struct PathStats { uint64_t singleSteps, pairedSteps; double denseFraction; bool singleMode; };
+    PathStats pathStats() const {          // which step path ran (single-step kernel / two-step launch pairs), last density probe
+        PathStats s{0, 0, 0.0, false};
+        int32_t m = 0;
+        ck(kob_path_stats(ctx_, &s.singleSteps, &s.pairedSteps, &s.denseFraction, &m), "kob_path_stats");
+        s.singleMode = m != 0;
+        return s;
+    }
     uint64_t stepCounter() const { uint64_t s = 0; ck(kob_get_step_counter(ctx_, &s), "kob_get_step_counter"); return s; }
     int nx() const { return nx_; }
     int ny() const { return ny_; }
