@@ -279,7 +279,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
     f.job_base = c->job_expected;
     // adaptive policy, single-step mode: every 8th launch counts its live jobs (read back asynchronously)
-    const bool probe = c->fast2 == 2 && c->single_mode && !c->count_pending && (c->launches & 7) == 0;
+    const bool probe = c->single_mode && !c->count_pending && (c->launches & 7) == 0;
     unsigned int* live_ctr = reinterpret_cast<unsigned int*>(c->base + c->L.off_ticket + 32);
     if (probe) {
         KOB_CUDA(c, cudaMemsetAsync(live_ctr, 0, sizeof(unsigned int), c->stream));
@@ -377,7 +377,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         c->launches += 1;
         f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;
         kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
-        if (c->fast2 == 2 && !c->count_pending && c->h_count) {          // density probe for the adaptive policy
+        if (!c->count_pending && c->h_count) {                            // density probe (adaptive policy / kob_path_stats)
             KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
             KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
             c->count_pending = true;
@@ -394,7 +394,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
 
 // Can the next two sub-steps go through the two-step kernel?
 bool fast2_eligible(const kob_ctx* c) {
-    return c->kernel == KOB_KERNEL_FAST && c->prec == KOB_F32 && c->fast2 && c->fast_np == 1 && !c->noise_field &&
+    return c->kernel == KOB_KERNEL_FAST && c->prec == KOB_F32 && c->fast_np == 1 && !c->noise_field &&
            c->nx >= 8 && c->ny >= 8;
 }
 
@@ -599,7 +599,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) { c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_)); c->fast_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
-        if (const char* e_ = std::getenv("KOB_FAST2")) c->fast2 = std::min(2, std::max(0, std::atoi(e_)));
+        if (const char* e_ = std::getenv("KOB_FAST2")) { c->fast2 = std::min(2, std::max(0, std::atoi(e_))); c->single_mode = c->fast2 == 0; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) { c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_)); c->fast2_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
@@ -670,22 +670,31 @@ int kob_get_params(const kob_ctx* c, kob_params* p) {
     return KOB_OK;
 }
 
+// Fold a landed density probe into the policy state (non-blocking).
+// Break-even of the two paths (B200, 16384^2): a pair costs ~0.73 ms + 20 ms x g (general pass at 8 warps/SM), two single
+// steps ~2 x (0.69 + 1.65 g) ms, g = fraction of row ranges with crystal  ->  g ~ 0.04.  The single-step probe counts jobs
+// under a set theta flag (128 x 32 blocks), which over-estimates g: that is the hysteresis.
+void poll_density_probe(kob_ctx* c) {
+    constexpr double FAST2_TO_SINGLE = 0.04, FAST2_TO_PAIR = 0.04;
+    if (!c->count_pending || cudaEventQuery(c->ev_count) != cudaSuccess) return;
+    c->count_pending = false;
+    c->general_frac = (double)c->h_count[0] / (double)c->count_total;
+    if (c->fast2 == 2 && !c->linked) {
+        if (!c->single_mode && c->general_frac > FAST2_TO_SINGLE) c->single_mode = true;
+        else if (c->single_mode && c->general_frac < FAST2_TO_PAIR) c->single_mode = false;
+    }
+}
+
 int kob_step(kob_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
-    // Break-even of the two paths (B200, 16384^2): a pair costs ~0.73 ms + 20 ms x g (general pass at 8 warps/SM), two single
-    // steps ~2 x (0.69 + 1.65 g) ms, g = fraction of row ranges with crystal  ->  g ~ 0.04.  The single-step probe counts
-    // jobs under a set theta flag (128 x 32 blocks), which over-estimates g: that is the hysteresis.
-    constexpr double FAST2_TO_SINGLE = 0.04, FAST2_TO_PAIR = 0.04;
     for (int64_t s = 0; s < nsteps;) {
-        if (c->count_pending && cudaEventQuery(c->ev_count) == cudaSuccess) {       // a density probe has landed
-            c->count_pending = false;
-            c->general_frac = (double)c->h_count[0] / (double)c->count_total;
-            if (!c->single_mode && c->general_frac > FAST2_TO_SINGLE) c->single_mode = true;
-            else if (c->single_mode && c->general_frac < FAST2_TO_PAIR) c->single_mode = false;
-        }
-        const bool adaptive = c->fast2 == 2 && !c->linked;     // linked strips must all run the same launch sequence
-        if (nsteps - s >= 2 && fast2_eligible(c) && !(adaptive && c->single_mode)) {
+        poll_density_probe(c);
+        // KOB_FAST2 / kob_set_path_mode: 0 = single-step kernel, 1 = pairs, 2 = adaptive.  Linked strips must all run the same
+        // launch sequence, so "adaptive" means pairs there unless the caller (StripRing) agrees on a mode across the ring
+        // and sets it on every strip.
+        const bool want_single = c->fast2 == 0 || (c->fast2 == 2 && !c->linked && c->single_mode);
+        if (nsteps - s >= 2 && fast2_eligible(c) && !want_single) {
             KOB_TRY(launch_two_steps_fast(c));                  // temporal blocking: two sub-steps per launch pair
             s += 2; c->n_paired += 2;
         } else {
@@ -729,6 +738,7 @@ int kob_sync(kob_ctx* c) {
     if (!c) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    poll_density_probe(c);
     return check_fault(c);
 }
 
@@ -797,6 +807,12 @@ int kob_render_rgba(kob_ctx* c, uint8_t* rgba) {
 
 int kob_sim_frame(const kob_ctx* c, int64_t* f) { if (!c || !f) return KOB_ERR_INVALID_ARG; *f = c->frames; return KOB_OK; }
 int kob_sim_time_ms(const kob_ctx* c, double* ms) { if (!c || !ms) return KOB_ERR_INVALID_ARG; *ms = c->sim_ms; return KOB_OK; }
+int kob_set_path_mode(kob_ctx* c, int32_t mode) {
+    if (!c || mode < 0 || mode > 2) return KOB_ERR_INVALID_ARG;
+    c->fast2 = mode;
+    c->single_mode = mode == 0;        // single-step launches probe the live-job fraction, pairs the work-list length
+    return KOB_OK;
+}
 int kob_path_stats(const kob_ctx* c, uint64_t* single_steps, uint64_t* paired_steps, double* dense_fraction, int32_t* single_mode) {
     if (!c) return KOB_ERR_INVALID_ARG;
     if (single_steps) *single_steps = c->n_single;

@@ -253,6 +253,10 @@ class Kobayashi:
         self._ck(self._L.kob_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def set_path_mode(self, mode: int):
+        """0 single-step kernel, 1 two-step launch pairs, 2 adaptive.  Never changes results."""
+        self._ck(self._L.kob_set_path_mode(self._h, int(mode)))
+
     def path_stats(self) -> dict:
         """Sub-steps done by the single-step kernel / by two-step launch pairs, last density probe, policy mode."""
         a, b, fr, m = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_int32()

@@ -65,6 +65,15 @@ def exchange_blobs(blob: bytes, rank: int, world: int, device=None) -> List[byte
     return [bytes(o.cpu().tolist()) for o in outs]
 
 
+def next_path_mode(mode: int, dense_fraction: float, to_single: float, to_pairs: float) -> int:
+    """Ring-wide step-path policy with hysteresis: 1 = two-step launch pairs (sparse field), 0 = single-step kernel."""
+    if mode == 1 and dense_fraction > to_single:
+        return 0
+    if mode == 0 and dense_fraction < to_pairs:
+        return 1
+    return mode
+
+
 class StripRing:
     """This rank's strip of an nx x ny_global torus, linked to its ring neighbours.
 
@@ -84,6 +93,7 @@ class StripRing:
             def make_strip(y0, ny):
                 return Kobayashi(nx, ny, timeStep, device=device, ny_global=ny_global, y0=y0, **kw)
         self.strip = make_strip(self.y0, self.ny)
+        self._mode, self._since_vote = 1, 0                         # ring-wide step path: pairs first (as the library does)
         if world > 1:
             import torch
             import torch.distributed as dist
@@ -112,8 +122,31 @@ class StripRing:
             self.strip.add_nucleus(x, y)
         self.refresh()
 
+    # Linked strips must run the same launch sequence, so the library's own adaptive choice between the single-step kernel
+    # and two-step launch pairs is off inside a ring (pairs always).  The ring restores it: every POLICY_CHUNK sub-steps
+    # the strips' density probes are max-reduced and every rank switches the mode on the same sub-step.
+    POLICY_CHUNK = 64
+    TO_SINGLE, TO_PAIRS = 0.04, 0.03
+
     def step(self, n: int = 1):
-        self.strip.step(n)
+        if self.world == 1 or not hasattr(self.strip, "set_path_mode") or getattr(self.strip, "kernel", "") != "fast":
+            self.strip.step(n)
+            return
+        import torch
+        import torch.distributed as dist
+        while n > 0:
+            k = min(n, self.POLICY_CHUNK - self._since_vote)
+            self.strip.step(k)
+            n -= k
+            self._since_vote += k
+            if self._since_vote >= self.POLICY_CHUNK:
+                self._since_vote = 0
+                self.strip.sync()                                   # the asynchronous density probe has landed (and is folded in)
+                t = torch.tensor([self.strip.path_stats()["dense_fraction"]], dtype=torch.float64,
+                                 device="cuda" if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                self._mode = next_path_mode(self._mode, float(t[0]), self.TO_SINGLE, self.TO_PAIRS)
+                self.strip.set_path_mode(self._mode)
 
     def close(self):
         if self.world > 1:

@@ -154,6 +154,11 @@ int kob_sim_time_ms(const kob_ctx* ctx, double* ms);         /* _simTime,  src/K
 int kob_launch_count(const kob_ctx* ctx, uint64_t* launches);/* kernels launched by this context so far */
 /* Step-path bookkeeping (no reference counterpart): sub-steps done by the single-step kernel and by two-step launch
  * pairs so far, the last density probe (fraction of jobs with data-dependent work) and the adaptive policy's mode. */
+/* Select the step path at run time: 0 single-step kernel, 1 two-step launch pairs, 2 adaptive (the default; KOB_FAST2
+ * sets the initial value).  Strips of one ring must all be given the same mode at the same step (StripRing does that from
+ * an all-reduced density probe); results never depend on it. */
+enum { KOB_PATH_SINGLE = 0, KOB_PATH_PAIRS = 1, KOB_PATH_ADAPTIVE = 2 };
+int kob_set_path_mode(kob_ctx* ctx, int32_t mode);
 int kob_path_stats(const kob_ctx* ctx, uint64_t* single_steps, uint64_t* paired_steps, double* dense_fraction, int32_t* single_mode);
 int kob_get_dims(const kob_ctx* ctx, int64_t* nx, int64_t* ny, int64_t* ny_global, int64_t* y0);
 const char* kob_last_error(const kob_ctx* ctx);              /* ctx may be NULL: last create error */

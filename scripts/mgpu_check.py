@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--ny", type=int, default=257)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--noise", type=float, default=0.01)
+    ap.add_argument("--dense", action="store_true", help="dense (developed) field: exercises the ring-wide step-path policy")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -38,6 +39,11 @@ def main():
     for (y0, ny) in ring.parts:
         pos += [(a.nx // 3, y0), (2 * a.nx // 3, (y0 + ny - 1) % a.ny), (0, (y0 + 1) % a.ny), (a.nx - 1, (y0 - 2) % a.ny)]
     ring.seed_nuclei(pos)
+    if a.dense:
+        import bench
+        phi, t = bench.dense_state(a.nx, ring.ny, ring.y0)
+        ring.strip.set_fields(phi, t, np.zeros_like(phi))
+        ring.refresh()
     for _ in range(a.steps // 10):
         ring.step(10)
     ring.step(a.steps % 10)
@@ -56,8 +62,12 @@ def main():
                 single.clear()
                 for (x, y) in pos:
                     single.add_nucleus(x, y)
+                if a.dense:
+                    phi, t = bench.dense_state(a.nx, a.ny, 0)
+                    single.set_fields(phi, t, np.zeros_like(phi))
                 single.step(a.steps)
                 want = single.fields()
+                print(f"[mgpu_check] step paths: ring rank 0 {ring.strip.path_stats()}, single GPU {single.path_stats()}", flush=True)
             same = np.array_equal(got.view(np.uint8), want[k].view(np.uint8))
             print(f"[mgpu_check] world={world} {a.kernel}/{a.precision} {a.nx}x{a.ny} steps={a.steps} {name}: "
                   f"bitwise={same} maxabs={np.abs(got.astype(np.float64) - want[k].astype(np.float64)).max():.3e}", flush=True)

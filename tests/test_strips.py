@@ -112,3 +112,70 @@ def test_two_rank_gloo_strips_equal_single_domain(po, tmp_path, prec, noise_a, n
         got = np.concatenate([p[f"arr_{k}"] for p in parts], axis=0)
         assert bit_equal(got, want[k])
     assert [n for _, n in partition(nyg, world)] == [p["arr_0"].shape[0] for p in parts]
+
+
+# ---------------------------------------------------------------------------------------------- ring-wide step path
+def test_next_path_mode_hysteresis():
+    from crystalgrowth_b200.strips import next_path_mode
+    assert next_path_mode(1, 0.01, 0.04, 0.03) == 1 and next_path_mode(1, 0.05, 0.04, 0.03) == 0
+    assert next_path_mode(0, 0.035, 0.04, 0.03) == 0 and next_path_mode(0, 0.02, 0.04, 0.03) == 1
+
+
+class _MockStrip:
+    """Records the launch sequence a strip would run; its density probe is scripted per rank."""
+    kernel = "fast"
+
+    def __init__(self, density):
+        self.density, self.log, self.steps, self.mode = density, [], 0, 1
+
+    def step(self, n):
+        self.log.append((self.mode, n))
+        self.steps += n
+
+    def sync(self):
+        pass
+
+    def path_stats(self):
+        return {"dense_fraction": self.density(self.steps)}
+
+    def set_path_mode(self, mode):
+        self.mode = mode
+
+    def ipc_export(self):
+        return bytes(128)
+
+    def ipc_link(self, lo, hi):
+        pass
+
+    def halo_refresh(self):
+        pass
+
+
+def _policy_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from crystalgrowth_b200.strips import StripRing
+    # rank 1's strip becomes dense after 100 sub-steps and sparse again after 300; rank 0's never does
+    density = (lambda s: 0.0) if rank == 0 else (lambda s: 0.5 if 100 <= s < 300 else 0.0)
+    ring = StripRing(64, 64, 1e-4, rank=rank, world=world, make_strip=lambda y0, ny: _MockStrip(density))
+    for n in (10, 70, 1, 200, 37, 130):
+        ring.step(n)
+    np.save(os.path.join(out_dir, f"p{rank}.npy"), np.array(ring.strip.log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ring_agrees_on_the_step_path(tmp_path):
+    """Linked strips must run identical launch sequences: the ring max-reduces the density probes every 64 sub-steps and
+    every rank switches between pairs (1) and the single-step kernel (0) on the same sub-step — although only ONE
+    rank's strip is dense."""
+    world = 2
+    mp.spawn(_policy_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    logs = [np.load(os.path.join(tmp_path, f"p{r}.npy")) for r in range(world)]
+    assert np.array_equal(logs[0], logs[1])
+    modes = [int(m) for m, _ in logs[0]]
+    assert modes[0] == 1 and 0 in modes and modes[-1] == 1            # pairs -> single (rank 1 dense) -> pairs again
+    assert sum(int(n) for _, n in logs[0]) == 10 + 70 + 1 + 200 + 37 + 130
+    assert all(int(n) <= 64 for _, n in logs[0])
