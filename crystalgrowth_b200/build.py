@@ -61,6 +61,21 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Development: the same library with other compile-time knobs (-DKOB_FAST_WARPS=12 ...), loaded through
+    KOB_LIB_PATH (see _lib.py).  Output: crystalgrowth_b200/variants/libkobayashi_cuda_<name>.so (git-ignored)."""
+    out_dir = os.path.join(PKG, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libkobayashi_cuda_{name}.so")
+    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-Xptxas=-v", "-ccbin", _host_cxx(), "-shared", "-o", out, os.path.join(CSRC, "kob_api.cu")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    with open(out + ".log", "w") as fh:
+        fh.write(r.stdout)
+    return out
+
+
 def build_driver(force: bool = False) -> str:
     src = os.path.join(PKG, "driver", "kob_bench.cpp")
     hdrs = [src, os.path.join(ROOT, "include", "kobayashi_c.h"), os.path.join(ROOT, "include", "Kobayashi.hpp")]
@@ -79,5 +94,9 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(LIB)

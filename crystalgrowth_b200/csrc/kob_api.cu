@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/kobayashi_c.h"
 #include "kob_aux.cuh"
@@ -90,7 +91,10 @@ struct kob_ctx {
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
     FastMaps maps{}, maps2{}, maps_far{};   // single-step boxes; two-step boxes (72 wide); far pass: phi 64 wide + T 72 wide
-    int fast_np = 1, fast_yj = 64, fast_yj_b = 32;
+    int fast_yj = 64, fast_yj_b = 32;
+    int fast_dense = 1;           // straight-line dense tier of the single-step kernel: 0 off, 1 predicted, 2 always (test knob)
+    int nsm = 0;                  // SMs of the device
+    std::unordered_map<const void*, int> occ;   // resident CTAs per SM of each kernel instantiation this context launched
     bool fast_yj_env = false, fast2_yj_env = false;   // job heights given explicitly: no automatic shortening
     double fast_frac_a = 0.9;
     int fast_cta_jobs = 2;        // CTA-wide jobs: 8 adjacent strips (1920 B contiguous per row); 2 = lock-step only on far-field jobs
@@ -201,7 +205,7 @@ int build_fast_maps(kob_ctx* c) {
         q != cudaDriverEntryPointSuccess)
         return fail(c, KOB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
-    const int bw = c->fast_np == 2 ? FastGeom<2>::BW : FastGeom<1>::BW;
+    const int bw = FastGeom::BW;
     const cuuint64_t dims[2] = {(cuuint64_t)c->L.pitch, (cuuint64_t)c->L.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)c->L.pitch * 4};
     const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)FAST_RB};
@@ -233,6 +237,21 @@ int build_fast_maps(kob_ctx* c) {
 
 
 
+// Resident CTAs per SM of a kernel (and the opt-in to its dynamic shared memory), cached per context: a context is driven by
+// one host thread at a time, so there is no shared mutable state between contexts stepped from different threads.
+int kernel_occupancy(kob_ctx* c, const void* kern, int threads, int smem, int* out) {
+    auto it = c->occ.find(kern);
+    if (it == c->occ.end()) {
+        int cps = 0;
+        KOB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, threads, smem));
+        if (cps < 1) return fail(c, KOB_ERR_CUDA, "kernel does not fit on an SM");
+        it = c->occ.emplace(kern, cps).first;
+    }
+    *out = it->second;
+    return KOB_OK;
+}
+
 // Rows per job: the configured height or a shorter one (halvings down to 4) — whichever minimises the serial work of the
 // busiest warp, rounds x (rows + warm-up rows).  On big grids that is the configured height; on small ones the jobs shrink
 // until every warp of the persistent grid has one.  Not applied when the height was set explicitly (environment).
@@ -248,21 +267,14 @@ int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps
     return std::max(4, best / 4 * 4);
 }
 
-template <int NP, int JM, bool NOISE, bool ROT>
+template <int JM, int NOISE, bool ROT>
 int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
-    auto kern = kob_step_fast<NP, JM, NOISE, ROT>;
-    constexpr int FAST_WARPS = fast_warps<NP>();
-    const int smem = FAST_WARPS * fast_warp_bytes<NP>() + FAST_WARPS * FAST_NST * 8;
-    static int ctas_per_sm[64] = {0};   // per device
-    int& cps = ctas_per_sm[c->device & 63];
-    if (cps == 0) {
-        KOB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, FAST_WARPS * 32, smem));
-        if (cps < 1) return fail(c, KOB_ERR_CUDA, "FAST kernel does not fit on an SM");
-    }
-    int nsm = 0;
-    KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-    f.nstrips = (int)((c->nx + FastGeom<NP>::OUTC - 1) / FastGeom<NP>::OUTC);
+    auto kern = kob_step_fast<JM, NOISE, ROT>;
+    const int smem = FAST_WARPS * FAST_WARP_BYTES + FAST_WARPS * FAST_NST * 8;
+    int cps = 0;
+    KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kern), FAST_WARPS * 32, smem, &cps));
+    const int nsm = c->nsm;
+    f.nstrips = (int)((c->nx + FastGeom::OUTC - 1) / FastGeom::OUTC);
     // guided job heights: fast_yj rows for the first fast_frac_a of the strip, fast_yj_b rows for the rest; on small
     // grids the jobs are made shorter until every warp of the persistent grid has one (a warp marches its job serially:
     // 250^2 with 64-row jobs is 20 warps at work, 62 us per launch; with 4-row jobs 12 us).  Bit-neutral.
@@ -274,7 +286,16 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
     f.cta_jobs = f.nstrips < FAST_WARPS ? 0 : c->fast_cta_jobs;   // narrow grids: a CTA job would be mostly padding warps
     f.no_skip = c->fast_no_skip;
+    f.dense_mode = c->fast_dense;
     f.nstrips_p = (f.nstrips + FAST_WARPS - 1) / FAST_WARPS * FAST_WARPS;
+    // linked strips: how many jobs touch the low / high seam (the kernel publishes a side when its jobs are done)
+    f.seam_jobs[0] = f.seam_jobs[1] = 0;
+    for (int seg = 0; seg < f.nseg; ++seg) {
+        const long long y0 = seg < f.nseg_a ? (long long)seg * f.yj : (long long)f.nseg_a * f.yj + (long long)(seg - f.nseg_a) * f.yj_b;
+        const long long y1 = std::min<long long>(y0 + (seg < f.nseg_a ? f.yj : f.yj_b), c->ny);
+        if (y0 < GY + 1) f.seam_jobs[0] += (unsigned)f.nstrips;
+        if (y1 > c->ny - GY - 1) f.seam_jobs[1] += (unsigned)f.nstrips;
+    }
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     const int grid = (int)std::min<long long>((long long)nsm * cps, (njobs + FAST_WARPS - 1) / FAST_WARPS);
     f.job_base = c->job_expected;
@@ -300,20 +321,36 @@ FastArgs fast_args_of(kob_ctx* c, const StepArgs<float>& a) {
     const KParams<float>& P = a.prm;
     FastArgs f{};
     f.job_ctr = reinterpret_cast<unsigned long long*>(c->base + c->L.off_ticket + 8);
+    f.seam_ctr = reinterpret_cast<unsigned int*>(c->base + c->L.off_ticket + 40);
+    ColdK& K = f.ck;
+    K.e = REF_DEADBAND;
+    // re-assigned angle = quadrant offset + atan(w), w in [-1, 1] (kob_row.cuh): the reference's branch offsets
+    // 0 / PI_F / 2 PI_F (src/Kobayashi.cpp:160-167) with the +-pi/4 of the argument fold
+    const double q4 = 0.78539816339744830962, pif = (double)REF_PI_F;
+    K.off1 = (float)q4; K.off2 = (float)(pif - q4); K.off3 = (float)(pif + q4); K.off4 = (float)(2.0 * pif - q4);
+    K.half_pi = 0.5f * REF_PI_F;
     // eps, eps' of a cell that holds theta = 0 (far field), evaluated like src/Kobayashi.cpp:170-171
     const double arg0 = (double)P.aniso * (0.0 - (double)P.theta0);
     volatile float c0 = (float)std::cos(arg0), s0 = (float)std::sin(arg0);
     volatile float dc = P.delta * c0;
     volatile float one_dc = 1.0f + dc;
-    f.eps0 = P.epsbar * one_dc;
-    f.epsd0 = P.neg_ebjd * s0;
-    f.cj0 = (float)std::cos((double)P.aniso * (double)P.theta0);
-    f.sj0 = (float)std::sin((double)P.aniso * (double)P.theta0);
-    f.ebd = P.epsbar * P.delta;
-    f.il_dt = P.inv_lapden * P.dt;
-    f.two_pi = 2.0f * REF_PI_F;
-    f.half_pi = 0.5f * REF_PI_F;
-    f.m_off = P.alpha_over_pi * 1.57079632679489662f;
+    K.eps0 = P.epsbar * one_dc;
+    K.epsd0 = P.neg_ebjd * s0;
+    K.cj0 = (float)std::cos((double)P.aniso * (double)P.theta0);
+    K.sj0 = (float)std::sin((double)P.aniso * (double)P.theta0);
+    K.ebd = P.epsbar * P.delta;
+    K.epsbar = P.epsbar;
+    K.neg_ebjd = P.neg_ebjd;
+    K.neg_gamma = -P.gamma;
+    K.gamma_teq = P.gamma * P.teq;
+    K.aop = P.alpha_over_pi;
+    K.m_q = (float)((double)P.alpha_over_pi * q4);
+    K.noise_a = P.noise_a;
+    K.aniso = P.aniso; K.theta0 = P.theta0; K.jmode = P.jmode;
+    RowConst& R = f.rc;
+    R.idx = P.inv_dx; R.idy = P.inv_dy; R.il = P.inv_lapden; R.ildt = P.inv_lapden * P.dt; R.dtt = P.dt_over_tau; R.K = P.K;
+    volatile float a0 = K.eps0 * K.eps0, b0 = K.eps0 * K.epsd0;
+    R.A0 = a0; R.B0 = b0;
     for (int r = 0; r < 10; ++r) {
         f.pk[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
         f.pk[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -329,15 +366,9 @@ template <int JM, bool NOISE, bool ROT>
 int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     auto kern = kob_step_fast2<JM, NOISE, ROT>;
     const int smem = F2_WARPS * F2_WARP_BYTES + F2_WARPS * F2_NST * 8;
-    static int ctas_per_sm[64] = {0};   // per device
-    int& cps = ctas_per_sm[c->device & 63];
-    if (cps == 0) {
-        KOB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, F2_WARPS * 32, smem));
-        if (cps < 1) return fail(c, KOB_ERR_CUDA, "two-step FAST kernel does not fit on an SM");
-    }
-    int nsm = 0;
-    KOB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    int cps = 0;
+    KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kern), F2_WARPS * 32, smem, &cps));
+    const int nsm = c->nsm;
     f.nstrips = (int)((c->nx + F2_OUTC - 1) / F2_OUTC);
     f.yj = auto_job_rows(c->fast2_yj, c->fast2_yj_env, f.nstrips, c->ny, (long long)nsm * 3 * FAR2_WARPS, 8);
     f.yj_b = std::min(c->fast2_yj_b, f.yj);
@@ -358,14 +389,9 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         }
         unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim
         KOB_CUDA(c, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), c->stream));
-        static int far_cps[64] = {0};
-        int& fcps = far_cps[c->device & 63];
         const int far_smem = FAR2_WARPS * FAR2_WARP_BYTES + FAR2_WARPS * FAR2_NST * 8;
-        if (fcps == 0) {
-            KOB_CUDA(c, cudaFuncSetAttribute(kob_far2, cudaFuncAttributeMaxDynamicSharedMemorySize, far_smem));
-            KOB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fcps, kob_far2, FAR2_WARPS * 32, far_smem));
-            if (fcps < 1) return fail(c, KOB_ERR_CUDA, "far-pass kernel does not fit on an SM");
-        }
+        int fcps = 0;
+        KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kob_far2), FAR2_WARPS * 32, far_smem, &fcps));
         Far2Args w{c->worklist + 4, counters};
         FastArgs ff = f;
         ff.cta_jobs = f.nstrips < FAR2_WARPS ? 0 : c->fast2_far_cta;      // narrow grids: a CTA job would be mostly padding
@@ -394,7 +420,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
 
 // Can the next two sub-steps go through the two-step kernel?
 bool fast2_eligible(const kob_ctx* c) {
-    return c->kernel == KOB_KERNEL_FAST && c->prec == KOB_F32 && c->fast_np == 1 && !c->noise_field &&
+    return c->kernel == KOB_KERNEL_FAST && c->prec == KOB_F32 && !c->noise_field &&
            c->nx >= 8 && c->ny >= 8;
 }
 
@@ -423,20 +449,20 @@ int launch_step_fast(kob_ctx* c, const StepArgs<float>& a, bool noise) {
     const KParams<float>& P = a.prm;
     FastArgs f = fast_args_of(c, a);
     const bool rot = P.theta0 != 0.0f;
-    const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot ? P.jmode : 0);
-#define KOB_FAST_CASE(NP_, JM_, ROT_)                                                          \
-    return noise ? launch_fast_t<NP_, JM_, true, ROT_>(c, a, f) : launch_fast_t<NP_, JM_, false, ROT_>(c, a, f)
-#define KOB_FAST_NP(NP_)                                                                       \
-    do {                                                                                       \
-        if (jm == 4) { KOB_FAST_CASE(NP_, 4, false); }                                         \
-        if (jm == 6) { KOB_FAST_CASE(NP_, 6, false); }                                         \
-        if (jm == 0 && !rot) { KOB_FAST_CASE(NP_, 0, false); }                                 \
-        if (jm == 0 && rot) { KOB_FAST_CASE(NP_, 0, true); }                                   \
-        KOB_FAST_CASE(NP_, -1, false);                                                         \
-    } while (0)
-    if (c->fast_np == 2) KOB_FAST_NP(2);
-    KOB_FAST_NP(1);
-#undef KOB_FAST_NP
+    const bool field = noise && c->noise_field != nullptr;     // host-injected noise: the run-time-j instantiations only
+    const int jm = P.jmode < 0 ? -1 : ((P.jmode == 4 || P.jmode == 6) && !rot && !field ? P.jmode : 0);
+#define KOB_FAST_CASE(JM_, ROT_) \
+    return noise ? launch_fast_t<JM_, 1, ROT_>(c, a, f) : launch_fast_t<JM_, 0, ROT_>(c, a, f)
+    if (field) {
+        if (jm == 0 && !rot) return launch_fast_t<0, 2, false>(c, a, f);
+        if (jm == 0 && rot) return launch_fast_t<0, 2, true>(c, a, f);
+        return launch_fast_t<-1, 2, false>(c, a, f);
+    }
+    if (jm == 4) { KOB_FAST_CASE(4, false); }
+    if (jm == 6) { KOB_FAST_CASE(6, false); }
+    if (jm == 0 && !rot) { KOB_FAST_CASE(0, false); }
+    if (jm == 0 && rot) { KOB_FAST_CASE(0, true); }
+    KOB_FAST_CASE(-1, false);
 #undef KOB_FAST_CASE
 }
 
@@ -581,6 +607,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     auto bail = [&](int code, const std::string& m) { g_create_error = m; kob_destroy(c); return code; };
     cudaError_t e;
     if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
+    if ((e = cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
@@ -595,7 +622,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     c->upper.base = c->base; c->upper.ny = ny;
     if (c->kernel == KOB_KERNEL_FAST) {
         // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
-        if (const char* e_ = std::getenv("KOB_FAST_NP")) c->fast_np = std::atoi(e_) == 2 ? 2 : 1;
+        if (const char* e_ = std::getenv("KOB_FAST_DENSE")) c->fast_dense = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) { c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_)); c->fast_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;

@@ -43,214 +43,42 @@ constexpr int F2_BOX_FLOATS = (FAST_RB * F2_BW + 31) / 32 * 32;
 constexpr int F2_STAGE_FLOATS = 2 * F2_BOX_FLOATS;
 constexpr int F2_WARP_BYTES = F2_NST * F2_STAGE_FLOATS * 4;
 
-// Register windows of one level; "r" is the phi row this level consumes in the current iteration.
-struct F2Level {
-    float2 po0, po1;            // phi rows r-2, r-1
-    float2 gx1, gx2, gy2;       // gx(r-1); gx, gy (r-2)
-    float2 u1, lp1, lap2;       // u(r-1), c(r-1)+u(r-2), complete 9-point sum of row r-2
-    float2 tq1, tu1, tlp1;      // T(r-2), u_T(r-2), c_T(r-2)+u_T(r-3)      [T lags phi by a row]
-    float2 A2, A3, P2, P3, Q2;  // eps^2 (r-2, r-3), eps*eps'*gx (r-2, r-3), eps*eps'*gy (r-2)
-    uint32_t nxa, nxb;          // Philox words of the odd row, drawn at the even row
-    bool have_next;
-    __device__ __forceinline__ void clear() {
-        po0 = po1 = gx1 = gx2 = gy2 = u1 = lp1 = lap2 = tq1 = tu1 = tlp1 = A2 = A3 = P2 = P3 = Q2 = make_float2(0.f, 0.f);
-        nxa = nxb = 0u; have_next = false;
-    }
-};
-
-// Loop constants of the row update, broadcast to pairs once per job.
-struct F2Const {
-    float2 idx2, idy2, il2, ildt2, dtt2, K2, B02;
-    float A0, e, pi;
-};
-
-// T-only row of one level (far field: phi == +0 in the whole footprint): rotates the T windows, returns T+ of row r-2.
-__device__ __forceinline__ float2 f2_row_tonly(F2Level& S, const F2Const& C, float2 tn, float tw, float te) {
-    const float2 two2 = f2(2.0f), m12 = f2(-12.0f);
-    const float2 thsum = make_float2(tw + tn.y, tn.x + te);
-    const float2 tu_new = f2fma(two2, tn, thsum);
-    const float2 lapt = f2add(S.tlp1, tu_new);
-    const float2 nt = f2fma(C.K2, f2(0.f), f2fma(lapt, C.ildt2, S.tq1));           // :215 with phi+ - phi = +0
-    S.tlp1 = f2fma(two2, thsum, f2fma(m12, tn, S.tu1));
-    S.tu1 = tu_new;
-    S.tq1 = tn;
-    return nt;
-}
-
-// One full row of one level.  Inputs: phi row r (own pair pn, west, east), T row r-1 (tn, tw, te), th_old = angle a cell
-// of row r-1 keeps if the state machine holds it.  Outputs: phi+/T+ of row r-2, th_eff = angle of row r-1 after this
-// sub-step, any_asg |= some cell of row r-1 re-assigned.  `pc2/pc3` = Philox counter words (step) of this level,
-// `yglob` = global row of pass 2 (r-2), `even` = first row of a row pair (Philox sharing), `wrap_noise` = seam job.
+// One full row of one level (kob_row.cuh's row_full plus this kernel's noise addressing).  Inputs: phi row r (own pair pn,
+// west, east), T row r-1 (tn, tw, te), th_old_in = angle a cell of row r-1 keeps if the state machine holds it.  Outputs:
+// phi+/T+ of row r-2, th_eff = angle of row r-1 after this sub-step, any_asg |= some cell of row r-1 re-assigned.
+// `pc2/pc3` = Philox counter words (step) of this level, `yglob` = global row of pass 2 (r-2), `even` = first row of a row
+// pair (Philox sharing), `wrap_noise` = seam job.
 template <int JM, bool NOISE, bool ROT, bool GEN>
-__device__ __forceinline__ void f2_row(F2Level& S, const F2Const& C, const KParams<float>& P, const FastArgs& f, float2 pn,
-                                       float w, float ee, float2 tn, float tw, float te, const float (&th_old_in)[2],
-                                       uint32_t pc2, uint32_t pc3, int x, long long yglob, bool even, int lane, bool wrap_noise,
-                                       int nx, long long nyg, float2& np_, float2& nt_, float (&th_eff)[2], bool& any_asg) {
-    const float2 two2 = f2(2.0f), m12 = f2(-12.0f);
-    const float e = C.e, pi = C.pi;
-    const float A_w = __shfl_up_sync(0xffffffffu, S.A2.y, 1);
-    const float A_e = __shfl_down_sync(0xffffffffu, S.A2.x, 1);
-    const float Q_w = __shfl_up_sync(0xffffffffu, S.Q2.y, 1);
-    const float Q_e = __shfl_down_sync(0xffffffffu, S.Q2.x, 1);
-    // ---- phi row r: horizontal sums and x-gradient; T row r-1: horizontal sums ----
-    const float2 hsum = make_float2(w + pn.y, pn.x + ee);
-    const float2 gxn = f2mul(make_float2(pn.y - w, ee - pn.x), C.idx2);                       // :139
-    const float2 thsum = make_float2(tw + tn.y, tn.x + te);
-    // ---- pass 1 for row r-1, far-field values first ----
-    const float2 gyn = f2mul(f2sub(pn, S.po0), C.idy2);                                       // :140
-    float2 An = f2(C.A0), Pn = f2mul(C.B02, S.gx1), Qn = f2mul(C.B02, gyn);                   // cells holding theta = 0
-    const float2 q = f2fma(f2neg(S.po0), S.po0, S.po0);                                       // phi (1 - phi) of row r-2
-    float2 radd = f2(0.f);
-    bool asg[2];
-    asg[0] = (S.gx1.x < -e) || (fabsf(gyn.x) > e);                                            // :154-167: theta re-assigned
-    asg[1] = (S.gx1.y < -e) || (fabsf(gyn.y) > e);
-    bool interesting = asg[0] || asg[1] || q.x != 0.f || q.y != 0.f;
-    if (GEN) interesting |= th_old_in[0] != 0.f || th_old_in[1] != 0.f;
-    th_eff[0] = GEN ? th_old_in[0] : 0.f;
-    th_eff[1] = GEN ? th_old_in[1] : 0.f;
+__device__ __forceinline__ void f2_row(RowState& S, const FastArgs& f, float2 pn, float w, float ee, float2 tn, float tw, float te,
+                                       const float (&th_old_in)[2], uint32_t pc2, uint32_t pc3, int x, long long yglob, bool even,
+                                       int lane, bool wrap_noise, int nx, long long nyg, float2& np_, float2& nt_,
+                                       float (&th_eff)[2], bool& any_asg) {
+    auto draw = [&]() -> float2 {
+        if (wrap_noise) {
+            // seam job: level 1 also updates cells it does not own (ghost columns / rows of the torus); their draw must
+            // be the owner's, i.e. keyed on the WRAPPED global cell — one Philox block per cell, no sharing
+            long long yw = yglob;
+            yw = yw < 0 ? yw + nyg : (yw >= nyg ? yw - nyg : yw);
+            uint32_t wk[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                int xw = x + k;
+                xw = xw < 0 ? xw + nx : (xw >= nx ? xw - nx : xw);
+                const Philox4 ph = fast_philox(f, (uint32_t)xw >> 2, (uint32_t)yw, pc2, pc3);
+                const uint32_t i3 = (uint32_t)xw & 3u;
+                wk[k] = i3 == 0u ? ph.w[0] : (i3 == 1u ? ph.w[1] : (i3 == 2u ? ph.w[2] : ph.w[3]));
+            }
+            return f2fma(make_float2((float)(wk[0] >> 8), (float)(wk[1] >> 8)), f2(5.9604644775390625e-8f), f2(-0.5f));
+        }
+        return fast_draw_shared(f, S, x, (uint32_t)yglob, pc2, pc3, even, lane);
+    };
     if (even) S.have_next = false;
-    if (__any_sync(0xffffffffu, interesting)) {
-        float th_old[2];
-        th_old[0] = (GEN && !asg[0]) ? th_old_in[0] : 0.f;
-        th_old[1] = (GEN && !asg[1]) ? th_old_in[1] : 0.f;
-        const float2 gx = S.gx1, gy = gyn;
-        const float2 agx = make_float2(fabsf(gx.x), fabsf(gx.y)), agy = make_float2(fabsf(gy.x), fabsf(gy.y));
-        const float2 mn = make_float2(fminf(agx.x, agy.x), fminf(agx.y, agy.y));
-        const float2 mx = make_float2(fmaxf(agx.x, agy.x), fmaxf(agx.y, agy.y));
-        float2 r = atan01_2(f2mul(mn, make_float2(rcp_approx(mx.x), rcp_approx(mx.y))));
-        const bool sw0 = agy.x > agx.x, sw1 = agy.y > agx.y;
-        r = f2fma(r, make_float2(sw0 ? -1.0f : 1.0f, sw1 ? -1.0f : 1.0f), make_float2(sw0 ? HALF_PI_TRUE : 0.0f, sw1 ? HALF_PI_TRUE : 0.0f));
-        r.x = __uint_as_float(__float_as_uint(r.x) ^ ((__float_as_uint(gx.x) ^ __float_as_uint(gy.x)) & 0x80000000u));
-        r.y = __uint_as_float(__float_as_uint(r.y) ^ ((__float_as_uint(gx.y) ^ __float_as_uint(gy.y)) & 0x80000000u));
-        float2 th2 = f2add(make_float2(gx.x < 0.f ? pi : (gy.x < 0.f ? f.two_pi : 0.0f), gx.y < 0.f ? pi : (gy.y < 0.f ? f.two_pi : 0.0f)), r);
-        const float2 r2 = f2fma(gx, gx, f2mul(gy, gy));
-        const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-        float2 c1 = f2mul(gx, rinv), s1 = f2mul(gy, rinv);
-        const bool fl0 = asg[0] && agx.x <= e, fl1 = asg[1] && agx.y <= e;                    // case A (:154-158)
-        const bool rare = fl0 || fl1 || (GEN && (th_old[0] != 0.f || th_old[1] != 0.f));
-        if (__any_sync(0xffffffffu, rare)) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const bool fl = k ? fl1 : fl0;
-                const bool held = GEN && th_old[k] != 0.f;
-                const float sg = (k ? gy.y : gy.x) < 0.f ? -1.0f : 1.0f;
-                float t = th_old[k];
-                if (GEN) t = t > 3.14159265358979f ? fmaf(-1.0f, 6.28318548202514648f, t) + 1.74845553e-7f : t;
-                const float ct = GEN ? __cosf(t) : 0.f, st = GEN ? __sinf(t) : 0.f;
-                float& thk = k ? th2.y : th2.x;
-                float& ck = k ? c1.y : c1.x;
-                float& sk = k ? s1.y : s1.x;
-                thk = fl ? sg * f.half_pi : thk;
-                ck = fl ? 0.0f : (held ? ct : ck);
-                sk = fl ? sg : (held ? st : sk);
-            }
-        }
-        float2 Cc = f2(1.0f), Ss = f2(0.0f);
-        if (JM >= 0) {
-            if (JM == 0) cpow2_rt(P.jmode, c1, s1, Cc, Ss); else cpow2<(JM > 0 ? JM : 1)>(c1, s1, Cc, Ss);
-            if (ROT) {
-                const float2 c2 = f2fma(Cc, f2(f.cj0), f2mul(Ss, f2(f.sj0)));
-                const float2 s2 = f2fma(Ss, f2(f.cj0), f2neg(f2mul(Cc, f2(f.sj0))));
-                Cc = c2; Ss = s2;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const float th = asg[k] ? (k ? th2.y : th2.x) : th_old[k];
-                if (asg[k] || th != 0.f) {
-                    float Ck, Sk;
-                    fast_sincos(P.aniso * (th - P.theta0), &Sk, &Ck);
-                    if (k) { Cc.y = Ck; Ss.y = Sk; } else { Cc.x = Ck; Ss.x = Sk; }
-                }
-            }
-        }
-        th_eff[0] = asg[0] ? th2.x : th_eff[0];
-        th_eff[1] = asg[1] ? th2.y : th_eff[1];
-        any_asg |= asg[0] || asg[1];
-        float2 ep = f2fma(f2(f.ebd), Cc, f2(P.epsbar));                                       // :170
-        float2 ed = f2mul(f2(P.neg_ebjd), Ss);                                                // :171
-        const bool d0 = !asg[0] && !(GEN && th_old[0] != 0.f), d1 = !asg[1] && !(GEN && th_old[1] != 0.f);
-        ep = make_float2(d0 ? f.eps0 : ep.x, d1 ? f.eps0 : ep.y);
-        ed = make_float2(d0 ? f.epsd0 : ed.x, d1 ? f.epsd0 : ed.y);
-        An = f2mul(ep, ep);
-        const float2 B = f2mul(ep, ed);
-        Pn = f2mul(B, S.gx1);
-        Qn = f2mul(B, gyn);
-        // ---- reaction term q*((phi - 1/2) + m(T)) [+ noise] of row r-2, :206-214 ----
-        float2 rq = f2(0.f);
-        if (NOISE) {
-            const bool hi = (x & 2) != 0;
-            uint32_t wa, wb;
-            if (wrap_noise) {
-                // seam job: level 1 also updates cells it does not own (ghost columns / rows of the torus); their draw must
-                // be the owner's, i.e. keyed on the WRAPPED global cell — one Philox block per cell, no sharing
-                long long yw = yglob;
-                yw = yw < 0 ? yw + nyg : (yw >= nyg ? yw - nyg : yw);
-                uint32_t wk[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    int xw = x + k;
-                    xw = xw < 0 ? xw + nx : (xw >= nx ? xw - nx : xw);
-                    const Philox4 ph = fast_philox(f, (uint32_t)xw >> 2, (uint32_t)yw, pc2, pc3);
-                    const uint32_t i3 = (uint32_t)xw & 3u;
-                    wk[k] = i3 == 0u ? ph.w[0] : (i3 == 1u ? ph.w[1] : (i3 == 2u ? ph.w[2] : ph.w[3]));
-                }
-                wa = wk[0]; wb = wk[1];
-            } else if (even) {
-                const Philox4 ph = fast_philox(f, (uint32_t)x >> 2, (uint32_t)yglob + (hi ? 1u : 0u), pc2, pc3);
-                const int partner = hi ? lane - 1 : lane + 1;
-                const uint32_t ra = __shfl_sync(0xffffffffu, hi ? ph.w[0] : ph.w[2], partner);
-                const uint32_t rb = __shfl_sync(0xffffffffu, hi ? ph.w[1] : ph.w[3], partner);
-                wa = hi ? ra : ph.w[0]; wb = hi ? rb : ph.w[1];
-                S.nxa = hi ? ph.w[2] : ra; S.nxb = hi ? ph.w[3] : rb;
-                S.have_next = true;
-            } else if (S.have_next) {
-                wa = S.nxa; wb = S.nxb;
-            } else {
-                const Philox4 ph = fast_philox(f, (uint32_t)x >> 2, (uint32_t)yglob, pc2, pc3);
-                wa = hi ? ph.w[2] : ph.w[0]; wb = hi ? ph.w[3] : ph.w[1];
-            }
-            rq = f2fma(make_float2((float)(wa >> 8), (float)(wb >> 8)), f2(5.9604644775390625e-8f), f2(-0.5f));
-        }
-        const float2 xa = f2mul(f2(P.gamma), f2sub(f2(P.teq), S.tq1));
-        const float ax0 = fabsf(xa.x), ax1 = fabsf(xa.y);
-        const bool b0 = ax0 > 1.0f, b1 = ax1 > 1.0f;
-        const float2 ra_ = atan01_2(make_float2(b0 ? rcp_approx(ax0) : ax0, b1 ? rcp_approx(ax1) : ax1));
-        float2 m = f2fma(ra_, make_float2(b0 ? -P.alpha_over_pi : P.alpha_over_pi, b1 ? -P.alpha_over_pi : P.alpha_over_pi),
-                         make_float2(b0 ? f.m_off : 0.0f, b1 ? f.m_off : 0.0f));
-        m.x = __uint_as_float(__float_as_uint(m.x) ^ (__float_as_uint(xa.x) & 0x80000000u));
-        m.y = __uint_as_float(__float_as_uint(m.y) ^ (__float_as_uint(xa.y) & 0x80000000u));
-        float2 rv = f2mul(q, f2add(f2sub(S.po0, f2(0.5f)), m));                               // :214
-        if (NOISE) rv = f2fma(f2mul(f2(P.noise_a), q), rq, rv);
-        radd = rv;
-    }
-    // ---- pass 2 for row r-2 ----
-    const float2 dA = make_float2(S.A2.y - A_w, A_e - S.A2.x);                                // :190-192
-    const float2 dQ = make_float2(Q_w - S.Q2.y, S.Q2.x - Q_e);                                // term2, :201-203
-    const float2 gEx = f2mul(dA, C.idx2);
-    const float2 gEy = f2mul(f2sub(An, S.A3), C.idy2);                                        // :193-195
-    float2 sm = f2fma(f2sub(Pn, S.P3), C.idy2, radd);                                         // term1 (:197-199) + reaction
-    sm = f2fma(dQ, C.idx2, sm);
-    sm = f2fma(S.A2, f2mul(S.lap2, C.il2), sm);                                               // eps^2 * lap(phi)
-    sm = f2fma(gEx, S.gx2, sm);                                                               // term3, :204
-    sm = f2fma(gEy, S.gy2, sm);
-    np_ = f2fma(sm, C.dtt2, S.po0);                                                           // :211
-    const float2 tu_new = f2fma(two2, tn, thsum);                                             // u_T(r-1)
-    const float2 lapt = f2add(S.tlp1, tu_new);                                                // 9-point sum of T at row r-2
-    nt_ = f2fma(C.K2, f2sub(np_, S.po0), f2fma(lapt, C.ildt2, S.tq1));                        // :215
-    // ---- rotate the windows ----
-    S.tlp1 = f2fma(two2, thsum, f2fma(m12, tn, S.tu1));
-    S.tu1 = tu_new;
-    S.tq1 = tn;
-    const float2 u_new = f2fma(two2, pn, hsum);
-    S.lap2 = f2add(S.lp1, u_new);
-    S.lp1 = f2fma(two2, hsum, f2fma(m12, pn, S.u1));
-    S.u1 = u_new;
-    S.gx2 = S.gx1; S.gy2 = gyn; S.gx1 = gxn;
-    S.po0 = S.po1; S.po1 = pn;
-    S.A3 = S.A2; S.A2 = An;
-    S.P3 = S.P2; S.P2 = Pn;
-    S.Q2 = Qn;
+    bool asg[2];
+    float2 th2;
+    row_full<JM, NOISE, ROT, GEN, false>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
+    th_eff[0] = asg[0] ? th2.x : (GEN ? th_old_in[0] : 0.f);
+    th_eff[1] = asg[1] ? th2.y : (GEN ? th_old_in[1] : 0.f);
+    any_asg |= asg[0] || asg[1];
 }
 
 // ---- far pass --------------------------------------------------------------------------------------------------
@@ -294,10 +122,6 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
     float* __restrict__ phi_out = a.self.phi[a.cur ^ 1];
     float* __restrict__ t_out = a.self.t[a.cur ^ 1];
     const long long pitch = a.pitch;
-    F2Const C;
-    C.idx2 = C.idy2 = C.il2 = C.dtt2 = C.B02 = f2(0.f);
-    C.ildt2 = f2(f.il_dt); C.K2 = f2(a.prm.K);
-    C.A0 = 0.f; C.e = 0.f; C.pi = 0.f;
     unsigned int gchunk = 0;
     __shared__ unsigned long long s_job;
     const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
@@ -365,7 +189,7 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             issued = min(NST, nch);
             if (lane == 0)
                 for (int c = 0; c < issued; ++c) issue(c);
-            F2Level L1, L2;
+            RowState L1, L2;
             L1.clear(); L2.clear();
             float2 t1_prev = f2(0.f);
             const long long o4 = pidx<float>(pitch, x, y0 - 8);
@@ -412,10 +236,10 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                     const unsigned int yrel = (unsigned int)(yrel0 + rr);
                     const float* row = stt + rr * BW;
                     const float2 tn = *reinterpret_cast<const float2*>(row);
-                    const float2 t1 = f2_row_tonly(L1, C, tn, row[-1], row[2]);          // T^1 of row r-2
+                    const float2 t1 = row_tonly(L1, f.rc, tn, row[-1], row[2]);          // T^1 of row r-2
                     const float tw2 = __shfl_up_sync(0xffffffffu, t1_prev.y, 1);
                     const float te2 = __shfl_down_sync(0xffffffffu, t1_prev.x, 1);
-                    const float2 t2 = f2_row_tonly(L2, C, t1_prev, tw2, te2);            // T^2 of row r-4
+                    const float2 t2 = row_tonly(L2, f.rc, t1_prev, tw2, te2);            // T^2 of row r-4
                     t1_prev = t1;
                     if (ok && yrel < nstore) {
                         if (!seam) {
@@ -477,16 +301,11 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
     }
     __syncwarp();
 
-    const KParams<float>& P = a.prm;
     const CUtensorMap* map_phi = a.cur ? &maps.phi[1] : &maps.phi[0];
     const CUtensorMap* map_t = a.cur ? &maps.t[1] : &maps.t[0];
     float* __restrict__ phi_out = a.self.phi[a.cur ^ 1];
     float* __restrict__ t_out = a.self.t[a.cur ^ 1];
     const long long pitch = a.pitch;
-    F2Const C;
-    C.idx2 = f2(P.inv_dx); C.idy2 = f2(P.inv_dy); C.il2 = f2(P.inv_lapden); C.ildt2 = f2(f.il_dt);
-    C.dtt2 = f2(P.dt_over_tau); C.K2 = f2(P.K); C.B02 = f2(f.eps0 * f.epsd0);
-    C.A0 = f.eps0 * f.eps0; C.e = REF_DEADBAND; C.pi = REF_PI_F;
     const uint32_t pc2b = (uint32_t)(a.step + 1ull), pc3b = (uint32_t)((a.step + 1ull) >> 32);   // level 2 = step + 1
     unsigned int gchunk = 0;
 
@@ -582,7 +401,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         bool assigned_any = false;
         auto body = [&](auto gen_tag) {
             constexpr bool GEN = decltype(gen_tag)::value;      // true: held theta is read, ragged edge + alias stores
-            F2Level L1, L2;
+            RowState L1, L2;
             L1.clear(); L2.clear();
             float2 t1_prev = f2(0.f);                    // T^1 of row r-3 (level 2's T input lags its phi input by a row)
             float thp0[2] = {0.f, 0.f}, thp1[2] = {0.f, 0.f};      // theta^0 of rows r-1, r (held cells of level 1)
@@ -629,10 +448,10 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                             const unsigned int yrel = (unsigned int)(yrel0 + rr);
                             const float* row = stt + rr * BW;
                             const float2 tn = *reinterpret_cast<const float2*>(row);
-                            const float2 t1 = f2_row_tonly(L1, C, tn, row[-1], row[2]);          // T^1 of row r-2
+                            const float2 t1 = row_tonly(L1, f.rc, tn, row[-1], row[2]);          // T^1 of row r-2
                             const float tw2 = __shfl_up_sync(0xffffffffu, t1_prev.y, 1);
                             const float te2 = __shfl_down_sync(0xffffffffu, t1_prev.x, 1);
-                            const float2 t2 = f2_row_tonly(L2, C, t1_prev, tw2, te2);            // T^2 of row r-4
+                            const float2 t2 = row_tonly(L2, f.rc, t1_prev, tw2, te2);            // T^2 of row r-4
                             t1_prev = t1;
                             if (yrel < nstore) {
                                 *reinterpret_cast<float2*>(pphi) = f2(0.f);
@@ -673,7 +492,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                     float2 p1, t1;
                     float th1[2];
                     bool dummy = false;
-                    f2_row<JM, NOISE, ROT, GEN>(L1, C, P, f, pn, row[-1], row[2], tn, trow[-1], trow[2], thp0, f.pc2, f.pc3, x,
+                    f2_row<JM, NOISE, ROT, GEN>(L1, f, pn, row[-1], row[2], tn, trow[-1], trow[2], thp0, f.pc2, f.pc3, x,
                                                 a.y0 + y0 + (int)yrel + 2, even, lane, GEN && seam, a.nx, f.ny_global, p1, t1, th1, dummy);
                     // ---- level 2: sub-step s+1 on phi^1 row r-2, T^1 row r-3 ----
                     const float pw = __shfl_up_sync(0xffffffffu, p1.y, 1);
@@ -683,7 +502,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                     float2 p2, t2;
                     float th2f[2];
                     bool asg2 = false;
-                    f2_row<JM, NOISE, ROT, true>(L2, C, P, f, p1, pw, pe, t1_prev, tw2, te2, e2, pc2b, pc3b, x,
+                    f2_row<JM, NOISE, ROT, true>(L2, f, p1, pw, pe, t1_prev, tw2, te2, e2, pc2b, pc3b, x,
                                                  a.y0 + y0 + (int)yrel, even, lane, GEN && seam, a.nx, f.ny_global, p2, t2, th2f, asg2);
                     t1_prev = t1;
                     // ---- stores: phi^2, T^2 of row r-4; final angle of row r-3 ----

@@ -1,0 +1,134 @@
+// cold_check.cpp — CPU check of the FAST kernels' data-dependent arithmetic (crystalgrowth_b200/csrc/kob_row.cuh,
+// compiled for the host with -DKOB_HOST_EMU) against the reference's own expressions (src/Kobayashi.cpp:154-171,
+// :206-214) evaluated with libm.  Build + run: tests/test_cold_math.py.  Prints "ok" or the first failures.
+//
+// What is checked, per random cell: the re-assigned angle (state machine incl. the dead-band case A), eps^2 and
+// eps*eps' for j = 4, 6 (double-angle closed forms), 3, 5, 8 (repeated squaring), j = 5 with theta0 (rotation), j = 5.5
+// (trig), held non-zero angles, cells holding theta = 0, and the reaction term with m(T) and noise.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "../../crystalgrowth_b200/csrc/kob_row.cuh"
+
+using namespace kob;
+
+static const float PI_F = 3.1415926f;
+
+struct Prm { float epsbar = 0.01f, delta = 0.05f, aniso = 6.0f, alpha = 0.9f, gamma = 10.0f, teq = 1.0f, theta0 = 0.0f, noise_a = 0.01f; };
+
+static ColdK make_k(const Prm& p) {
+    ColdK K{};
+    K.e = FLT_EPSILON;
+    const double q = 0.78539816339744830962;
+    K.off1 = (float)q; K.off2 = (float)((double)PI_F - q); K.off3 = (float)((double)PI_F + q); K.off4 = (float)(2.0 * (double)PI_F - q);
+    K.half_pi = 0.5f * PI_F;
+    K.ebd = p.epsbar * p.delta; K.epsbar = p.epsbar;
+    K.neg_ebjd = ((-p.epsbar) * p.aniso) * p.delta;
+    const double a0 = (double)p.aniso * (0.0 - (double)p.theta0);
+    K.eps0 = p.epsbar * (1.0f + p.delta * (float)std::cos(a0));
+    K.epsd0 = K.neg_ebjd * (float)std::sin(a0);
+    K.cj0 = (float)std::cos((double)p.aniso * p.theta0); K.sj0 = (float)std::sin((double)p.aniso * p.theta0);
+    K.neg_gamma = -p.gamma; K.gamma_teq = p.gamma * p.teq;
+    K.aop = p.alpha / PI_F; K.m_q = (float)((double)K.aop * q);
+    K.noise_a = p.noise_a; K.aniso = p.aniso; K.theta0 = p.theta0;
+    K.jmode = (p.aniso == std::floor(p.aniso)) ? (int)p.aniso : -1;
+    return K;
+}
+
+// the reference's state machine; returns true when the angle is re-assigned
+static bool ref_angle(float gx, float gy, float& th) {
+    const float e = FLT_EPSILON;
+    bool asg = false;
+    if (gx <= e && gx >= -e) {
+        if (gy < -e) { th = -0.5f * PI_F; asg = true; } else if (gy > e) { th = 0.5f * PI_F; asg = true; }
+    }
+    if (gx > e) {
+        if (gy < -e) { th = 2.0f * PI_F + std::atan(gy / gx); asg = true; } else if (gy > e) { th = std::atan(gy / gx); asg = true; }
+    }
+    if (gx < -e) { th = PI_F + std::atan(gy / gx); asg = true; }
+    return asg;
+}
+
+static int fails = 0;
+static void expect(bool ok, const char* what, double got, double want, double tol, float gx, float gy) {
+    if (!ok && fails++ < 20) std::printf("FAIL %s: got %.9g want %.9g (tol %g) at gx=%.9g gy=%.9g\n", what, got, want, tol, gx, gy);
+}
+
+template <int JM, bool ROT>
+static void run(const Prm& p, uint64_t seed, int n) {
+    const ColdK K = make_k(p);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    for (int it = 0; it < n; ++it) {
+        float g[2][2], thold[2], phi[2], T[2], r[2];
+        for (int k = 0; k < 2; ++k) {
+            const int kind = (int)(rng() % 16);
+            double mag = std::pow(10.0, 2.0 * U(rng) - 0.5);      // |g| from 3e-3 to 30
+            g[k][0] = (float)(mag * U(rng)); g[k][1] = (float)(mag * U(rng));
+            if (kind == 0) g[k][0] = 0.f;                         // case A
+            if (kind == 1) g[k][0] = (float)(1e-7 * U(rng));      // inside the dead-band
+            if (kind == 2) g[k][1] = (rng() & 1) ? 0.f : -0.f;    // gy = +-0
+            if (kind == 3) { g[k][0] = 0.f; g[k][1] = 0.f; }       // fully flat: held
+            if (kind == 4) { g[k][0] = (float)std::fabs(g[k][0]) + 1e-3f; g[k][1] = (float)(5e-8 * U(rng)); }   // gx > e, |gy| <= e: held
+            if (kind == 5) g[k][1] = g[k][0];                     // diagonals
+            if (kind == 6) g[k][1] = -g[k][0];
+            thold[k] = (rng() % 3 == 0) ? 0.f : (float)((U(rng) + 1.0) * 3.14159);   // carried angle in [0, 2 pi)
+            if (rng() % 11 == 0) thold[k] = -0.5f * PI_F;
+            phi[k] = (float)(0.5 + 0.6 * U(rng)); T[k] = (float)(0.5 + 1.2 * U(rng)); r[k] = (float)(0.5 * (U(rng) + 1.0));
+            if (rng() % 13 == 0) T[k] = p.teq;
+        }
+        bool asg[2]; float th_ref[2], th_in[2];
+        for (int k = 0; k < 2; ++k) {
+            th_ref[k] = thold[k];
+            asg[k] = ref_angle(g[k][0], g[k][1], th_ref[k]);
+            const bool mine = (g[k][0] < -K.e) || (std::fabs(g[k][1]) > K.e);
+            expect(mine == asg[k], "asg", mine, asg[k], 0, g[k][0], g[k][1]);
+            th_in[k] = asg[k] ? 0.f : thold[k];
+        }
+        const float2 gx = make_float2(g[0][0], g[1][0]), gy = make_float2(g[0][1], g[1][1]);
+        const float2 ph = make_float2(phi[0], phi[1]), tq = make_float2(T[0], T[1]);
+        const float2 q = f2fma(f2neg(ph), ph, ph), rq = make_float2(r[0] - 0.5f, r[1] - 0.5f);
+        float2 An, Bn, th2, radd;
+        cold_block<JM, true, ROT, true>(K, gx, gy, th_in, asg, ph, tq, q, rq, An, Bn, th2, radd);
+        for (int k = 0; k < 2; ++k) {
+            const float An_k = k ? An.y : An.x, Bn_k = k ? Bn.y : Bn.x, th_k = k ? th2.y : th2.x, ra_k = k ? radd.y : radd.x;
+            if (asg[k]) {
+                double d = std::fabs((double)th_k - (double)th_ref[k]);
+                if (JM >= 0) d = std::fmin(d, std::fabs(d - 2.0 * (double)PI_F));
+                expect(d <= 1.2e-6, "theta", th_k, th_ref[k], 1.2e-6, g[k][0], g[k][1]);
+            }
+            const float th = th_ref[k];
+            const float eps = p.epsbar * (1.0f + p.delta * std::cos(p.aniso * (th - p.theta0)));
+            const float epd = -p.epsbar * p.aniso * p.delta * std::sin(p.aniso * (th - p.theta0));
+            // eps ~ 1e-2, eps' up to 8e-3: 3e-10 absolute on the products is far inside the single-step budget
+            // (eps^2 lap dt/tau).  The trig-free path does not see the reference's PI_F deficit (pi - PI_F = 1.5e-7 per
+            // branch offset, times j in the argument): beyond the sliders' j <= 8 the allowance scales with j.
+            const double tol = p.aniso > 8.0f ? 3e-10 * p.aniso / 4.0 : 3e-10;
+            expect(std::fabs((double)An_k - (double)eps * eps) <= tol, "eps^2", An_k, (double)eps * eps, tol, g[k][0], g[k][1]);
+            expect(std::fabs((double)Bn_k - (double)eps * epd) <= tol, "eps*eps'", Bn_k, (double)eps * epd, tol, g[k][0], g[k][1]);
+            const float m = p.alpha / PI_F * std::atan(p.gamma * (p.teq - T[k]));
+            const double want = (double)(phi[k] * (1.0f - phi[k])) * ((double)(phi[k] - 0.5f + m) + (double)p.noise_a * (r[k] - 0.5f));
+            expect(std::fabs((double)ra_k - want) <= 1.5e-7, "reaction", ra_k, want, 1.5e-7, phi[k], T[k]);
+        }
+    }
+}
+
+int main() {
+    Prm p;
+    p.aniso = 6.0f; run<6, false>(p, 1, 400000);
+    p.aniso = 4.0f; run<4, false>(p, 2, 400000);
+    for (float j : {0.f, 1.f, 2.f, 3.f, 5.f, 6.f, 8.f, 16.f}) { p.aniso = j; run<0, false>(p, 3 + (int)j, 100000); }
+    p.aniso = 5.0f; p.theta0 = 0.3f; run<0, true>(p, 40, 200000);
+    p.aniso = 4.0f; p.theta0 = -1.1f; run<0, true>(p, 41, 200000);
+    p.aniso = 5.5f; p.theta0 = 0.0f; run<-1, false>(p, 50, 100000);
+    p.aniso = 2.5f; p.theta0 = 0.7f; run<-1, false>(p, 51, 100000);
+    Prm s; s.epsbar = 0.012f; s.delta = 0.03f; s.alpha = 1.1f; s.gamma = 15.0f; s.teq = 0.9f; s.aniso = 8.0f; s.noise_a = 0.02f;
+    run<0, false>(s, 60, 200000);
+    if (fails) { std::printf("%d failures\n", fails); return 1; }
+    std::printf("ok\n");
+    return 0;
+}

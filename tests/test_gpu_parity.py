@@ -397,8 +397,8 @@ def test_linked_strips_on_one_gpu_equal_single_domain(po, cg, kernel, prec, nstr
 
 # ---------------------------------------------------------------------------------------------- FAST variants
 @pytest.mark.parametrize("cta", [0, 1, 2])
-@pytest.mark.parametrize("np_", [1, 2])
-def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, np_):
+@pytest.mark.parametrize("dense", [0, 1, 2])
+def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, dense):
     """Chunks whose phi rows (and the 4 rows before them) are all +0 skip the phi arithmetic and only diffuse T.
     That must not change a single bit: run with the shortcut disabled (KOB_FAST_NOSKIP=1) and compare.  The grid
     is wide/tall enough for whole far-field jobs, partial ones next to the crystals, and heat (T != 0) diffusing
@@ -407,7 +407,7 @@ def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, np_):
         monkeypatch.setenv("KOB_FAST_NOSKIP", str(noskip))
         monkeypatch.setenv("KOB_FAST2", "0")             # the single-step kernel's shortcut is what is under test
         monkeypatch.setenv("KOB_FAST_CTA", str(cta))
-        monkeypatch.setenv("KOB_FAST_NP", str(np_))
+        monkeypatch.setenv("KOB_FAST_DENSE", str(dense))  # straight-line dense tier: never / predicted / always
         monkeypatch.setenv("KOB_FAST_YJ", "32")
         g = cg.Kobayashi(700, 300, 1e-4, kernel="fast", seed=11, noise_a=0.01)
         g.clear()
@@ -423,12 +423,12 @@ def test_fast_far_field_shortcut_is_bit_neutral(cg, monkeypatch, cta, np_):
 
 
 @pytest.mark.parametrize("cta", [0, 1, 2])
-@pytest.mark.parametrize("np_,yj", [(1, 8), (2, 256), (2, 12), (1, 5)])
+@pytest.mark.parametrize("np_,yj", [(1, 8), (2, 256), (0, 12), (1, 5)])
 def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj, cta):
-    """The FAST kernel's decomposition knobs (cells per lane, rows per job) do not change results: every variant
-    passes the single-step gate, and the job height is bit-neutral."""
+    """The FAST kernel's decomposition knobs (dense tier never / predicted / always, rows per job) do not change results:
+    every variant passes the single-step gate, and the knobs are bit-neutral against the (dense = predicted, 256-row) run."""
     def run(env_np, env_yj, nx=150, ny=90, steps=12):
-        monkeypatch.setenv("KOB_FAST_NP", str(env_np))
+        monkeypatch.setenv("KOB_FAST_DENSE", str(env_np))
         monkeypatch.setenv("KOB_FAST_YJ", str(env_yj))
         monkeypatch.setenv("KOB_FAST_CTA", str(cta))
         g = cg.Kobayashi(nx, ny, 1e-4, kernel="fast", seed=9, noise_a=0.01)
@@ -438,7 +438,7 @@ def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj, cta):
         g.step(steps)
         return g
     a = run(np_, yj).fields()
-    b = run(np_, 256).fields()
+    b = run(1, 256).fields()
     assert all(bit_equal(x, y) for x, y in zip(a, b))
     # single-step gate from an evolved oracle state
     o = po.Oracle(150, 90, po.default_params(noise_a=0.01), math=po.MATH_LIBM, seed=9)
@@ -446,7 +446,7 @@ def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj, cta):
     for (x, y) in [(0, 0), (75, 45), (149, 89), (30, 7), (120, 8)]:
         o.add_nucleus(x, y)
     o.step(30)
-    monkeypatch.setenv("KOB_FAST_NP", str(np_))
+    monkeypatch.setenv("KOB_FAST_DENSE", str(np_))
     monkeypatch.setenv("KOB_FAST_YJ", str(yj))
     g = cg.Kobayashi(150, 90, 1e-4, kernel="fast", seed=9, noise_a=0.01)
     g.set_fields(*o.fields())
