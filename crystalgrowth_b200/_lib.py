@@ -57,6 +57,7 @@ SIGNATURES = {
     "kob_render_rgba": (C.c_int, [_P, _P]),
     "kob_sim_frame": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "kob_sim_time_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "kob_set_sim_counters": (C.c_int, [_P, C.c_int64, C.c_double]),
     "kob_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "kob_set_path_mode": (C.c_int, [_P, C.c_int32]),
     "kob_path_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

@@ -834,6 +834,11 @@ int kob_render_rgba(kob_ctx* c, uint8_t* rgba) {
 
 int kob_sim_frame(const kob_ctx* c, int64_t* f) { if (!c || !f) return KOB_ERR_INVALID_ARG; *f = c->frames; return KOB_OK; }
 int kob_sim_time_ms(const kob_ctx* c, double* ms) { if (!c || !ms) return KOB_ERR_INVALID_ARG; *ms = c->sim_ms; return KOB_OK; }
+int kob_set_sim_counters(kob_ctx* c, int64_t frames, double ms) {
+    if (!c || frames < 0) return KOB_ERR_INVALID_ARG;
+    c->frames = frames; c->sim_ms = ms;
+    return KOB_OK;
+}
 int kob_set_path_mode(kob_ctx* c, int32_t mode) {
     if (!c || mode < 0 || mode > 2) return KOB_ERR_INVALID_ARG;
     c->fast2 = mode;

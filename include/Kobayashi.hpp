@@ -126,19 +126,22 @@ public:
         std::vector<unsigned char> buf(3 * n * e);
         const bool ok = std::fread(h, 1, 256, fp) == 256 && std::fread(buf.data(), 1, buf.size(), fp) == buf.size();
         std::fclose(fp);
-        uint32_t hb, eb; int64_t dims[4]; uint64_t sc, seed; kob_params p;
+        uint32_t hb, eb; int64_t dims[4], fr; uint64_t sc, seed; kob_params p;
         std::memcpy(&hb, h + 8, 4); std::memcpy(&eb, h + 12, 4); std::memcpy(dims, h + 16, 32);
-        std::memcpy(&sc, h + 48, 8); std::memcpy(&seed, h + 56, 8); std::memcpy(&p, h + 72, sizeof p);
+        std::memcpy(&sc, h + 48, 8); std::memcpy(&seed, h + 56, 8); std::memcpy(&fr, h + 64, 8); std::memcpy(&p, h + 72, sizeof p);
         if (!ok || std::memcmp(h, "KOBCKPT1", 8) != 0 || hb != 256) throw KobayashiError(KOB_ERR_INVALID_ARG, path + " is not a KOBCKPT1 checkpoint");
         if (eb != e || dims[0] != nx_ || dims[1] != ny_ || dims[2] != ny_global_ || dims[3] != y0_ || seed != seed_)
             throw KobayashiError(KOB_ERR_INVALID_ARG, "checkpoint " + path + " was written for another grid / precision / strip / seed");
         setParams(p);
         setFields(buf.data(), buf.data() + n * e, buf.data() + 2 * n * e);
+        sync();                                                    // kob_set_fields is asynchronous: buf must outlive the copies
         ck(kob_set_step_counter(ctx_, sc), "kob_set_step_counter");
+        setSimCounters(fr < 0 ? 0 : fr, simTimeMs());              // _simFrame continues; on a linked strip follow with kob_halo_refresh on every strip
     }
 
     // ---- bookkeeping (_simTime, _simFrame, src/Kobayashi.cpp:237-238) ----
     int64_t simFrame() const { int64_t f = 0; ck(kob_sim_frame(ctx_, &f), "kob_sim_frame"); return f; }
+    void setSimCounters(int64_t frames, double ms) { ck(kob_set_sim_counters(ctx_, frames, ms), "kob_set_sim_counters"); }
     double simTimeMs() const { double ms = 0; ck(kob_sim_time_ms(ctx_, &ms), "kob_sim_time_ms"); return ms; }
     uint64_t launchCount() const { uint64_t n = 0; ck(kob_launch_count(ctx_, &n), "kob_launch_count"); return n; }
     struct PathStats { uint64_t singleSteps, pairedSteps; double denseFraction; bool singleMode; };

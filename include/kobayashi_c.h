@@ -134,7 +134,10 @@ int kob_sync(kob_ctx* ctx);
 
 /* ---- field access (src/Kobayashi.cpp:315 reads _phi; set/get of all three arrays = exact checkpoint) -- */
 
-/* Any pointer may be NULL.  Buffers hold nx*ny elements of the context's precision, reference layout. */
+/* Any pointer may be NULL.  Buffers hold nx*ny elements of the context's precision, reference layout.
+ * kob_get_fields returns after the copies have landed.  kob_set_fields is ASYNCHRONOUS on the context's stream: with pinned
+ * buffers (kob_host_alloc) the caller must kob_sync before overwriting or freeing them (pageable buffers are staged before
+ * the call returns). */
 int kob_get_fields(kob_ctx* ctx, void* phi, void* t, void* angl);
 int kob_set_fields(kob_ctx* ctx, const void* phi, const void* t, const void* angl);
 /* Host-injected noise field r in [0,1) (nx*ny floats, reference layout) used instead of the Philox
@@ -151,6 +154,9 @@ int kob_render_rgba(kob_ctx* ctx, uint8_t* rgba);
 
 int kob_sim_frame(const kob_ctx* ctx, int64_t* frames);      /* _simFrame, src/Kobayashi.cpp:238 */
 int kob_sim_time_ms(const kob_ctx* ctx, double* ms);         /* _simTime,  src/Kobayashi.cpp:237 */
+/* Write _simFrame / _simTime: iResetSimulationState zeroes them AFTER the viewer's refresh (src/Kobayashi.cpp:247-248);
+ * a checkpoint resume restores them. */
+int kob_set_sim_counters(kob_ctx* ctx, int64_t frames, double ms);
 int kob_launch_count(const kob_ctx* ctx, uint64_t* launches);/* kernels launched by this context so far */
 /* Step-path bookkeeping (no reference counterpart): sub-steps done by the single-step kernel and by two-step launch
  * pairs so far, the last density probe (fraction of jobs with data-dependent work) and the adaptive policy's mode. */

@@ -201,6 +201,9 @@ def ref_lib(prec=32) -> C.CDLL:
             "ref_get_fields": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "ref_set_fields": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
             "ref_add_nucleus": [C.c_void_p, C.c_int, C.c_int], "ref_colors": [C.c_void_p, C.c_void_p],
+            "ref_gui_attach": [C.c_void_p], "ref_gui_command": [C.c_void_p, C.c_int],
+            "ref_gui_hscroll": [C.c_void_p, C.c_int, C.c_int, C.c_int], "ref_gui_frame": [C.c_void_p],
+            "ref_gui_colors": [C.c_void_p, C.c_void_p], "ref_gui_state": [C.c_void_p, C.c_void_p],
         }.items():
             getattr(L, name).restype = None
             getattr(L, name).argtypes = args
@@ -246,3 +249,19 @@ class Reference:
         rgb = np.empty((self.nx * self.ny, 3), self.dtype)
         self._L.ref_colors(self._h, _ptr(rgb))
         return rgb
+
+    # ---- the reference's control panel, driven headlessly (src/Kobayashi.cpp:383-629) ----
+    def gui_attach(self): self._L.ref_gui_attach(self._h)
+    def gui_command(self, com): self._L.ref_gui_command(self._h, int(com))
+    def gui_hscroll(self, index, code, pos=0): self._L.ref_gui_hscroll(self._h, int(index), int(code), int(pos))
+    def gui_frame(self): self._L.ref_gui_frame(self._h)
+
+    def gui_colors(self):
+        rgb = np.zeros((self.nx * self.ny, 3), self.dtype)
+        self._L.ref_gui_colors(self._h, _ptr(rgb))
+        return rgb
+
+    def gui_state(self):
+        out = np.zeros(20, np.float64)
+        self._L.ref_gui_state(self._h, _ptr(out))
+        return {"playing": bool(out[0]), "sim_frame": int(out[1]), "values": out[2:11].copy(), "positions": out[11:20].astype(int)}

@@ -35,7 +35,8 @@ enum : unsigned {
 };
 inline unsigned LOWORD(WPARAM w) { return (unsigned)(w & 0xffffu); }
 inline unsigned HIWORD(WPARAM w) { return (unsigned)((w >> 16) & 0xffffu); }
-template <typename... A> inline HWND CreateWindow(A...) { return nullptr; }
+// every created control gets its own (fake) handle: the reference tells its scrollbars apart by HWND (src/Kobayashi.cpp:557-573)
+template <typename... A> inline HWND CreateWindow(A...) { static HWND__ pool[512]; static int n = 0; return &pool[n++ % 512]; }
 template <typename... A> inline int EnableWindow(A...) { return 0; }
 template <typename... A> inline HWND GetDlgItem(A...) { return nullptr; }
 template <typename... A> inline int SetScrollRange(A...) { return 0; }
@@ -88,12 +89,17 @@ namespace Microsoft { namespace WRL {
 template <typename T> struct ComPtr { T* p = nullptr; T* operator->() const { return p; } };
 } }
 
-// ---- DXViewer app object: the three calls Kobayashi.cpp makes ----
+// ---- DXViewer app object: the three calls Kobayashi.cpp makes, with the viewer's semantics but no Direct3D
+// (ext/DXViewer/src/DX12App.cpp:124-127 resetSimulationState, :554-617 update, :619-... draw) ----
+class ISimulation;
 class DX12App {
 public:
-    void update() {}
+    void setSimulation(ISimulation* s);          // + iSetDXApp + iCreateObject, as DX12App::initialize does
+    void update();                               // if (iIsUpdated()) iUpdate(); then iUpdateConstantBuffer for every object
     void draw() {}
-    void resetSimulationState() {}
+    void resetSimulationState();                 // iResetSimulationState(_constantBuffer)
+    std::vector<ConstantBuffer> _constantBuffer;
+    ISimulation* _simulation = nullptr;
 };
 
 // ---- the plugin interface, same 20 virtuals as ISimulation.h:7-85, in portable C++ ----
@@ -121,3 +127,18 @@ public:
     virtual void iWMDestory(HWND hwnd) = 0;
     virtual ~ISimulation() {}
 };
+
+inline void DX12App::setSimulation(ISimulation* s) {
+    _simulation = s;
+    s->iSetDXApp(this);
+    _constantBuffer.clear();
+    s->iCreateObject(_constantBuffer);
+}
+inline void DX12App::update() {
+    if (!_simulation) return;
+    if (_simulation->iIsUpdated()) _simulation->iUpdate();
+    for (int i = 0; i < (int)_constantBuffer.size(); ++i) _simulation->iUpdateConstantBuffer(_constantBuffer, i);
+}
+inline void DX12App::resetSimulationState() {
+    if (_simulation) _simulation->iResetSimulationState(_constantBuffer);
+}

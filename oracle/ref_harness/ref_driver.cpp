@@ -76,4 +76,46 @@ void ref_colors(void* h, ref_real* rgb) {
     }
 }
 
+// ---- the reference's control panel driven headlessly (src/Kobayashi.cpp:383-629): one stand-in DX12App per object ----
+static DX12App* gui_of(Kobayashi* k, bool create) {
+    static std::vector<std::pair<Kobayashi*, DX12App*>> apps;
+    for (auto& a : apps) if (a.first == k) return a.second;
+    if (!create) return nullptr;
+    DX12App* app = new DX12App();
+    apps.push_back({k, app});
+    return app;
+}
+static HWND__ g_panel;
+// DX12App::initialize + WM_CREATE: iSetDXApp, iCreateObject, iWMCreate (creates the nine scrollbars)
+void ref_gui_attach(void* h) {
+    Kobayashi* k = static_cast<Kobayashi*>(h);
+    DX12App* app = gui_of(k, true);
+    app->setSimulation(k);
+    k->iWMCreate(&g_panel, nullptr);
+}
+// WM_COMMAND with LOWORD(wParam) = com: 9 Reset, 10 Play/Pause, 11 Stop, 12 Next step (enum COM, src/Kobayashi.h:70-77)
+void ref_gui_command(void* h, int com) { static_cast<Kobayashi*>(h)->iWMCommand(&g_panel, 0, (WPARAM)com, 0, nullptr); }
+// WM_HSCROLL from slider `index` (0 tau .. 8 tEq): code = SB_* request, pos = thumb position for SB_THUMBTRACK
+void ref_gui_hscroll(void* h, int index, int code, int pos) {
+    Kobayashi* k = static_cast<Kobayashi*>(h);
+    k->iWMHScroll(&g_panel, (WPARAM)((unsigned)code | ((unsigned)pos << 16)), (LPARAM)k->_crystalParameter[index].scrollbar, nullptr);
+}
+// one pass of the viewer's frame loop: DX12App::update (iUpdate when playing + all constant buffers) and draw
+void ref_gui_frame(void* h) { DX12App* app = gui_of(static_cast<Kobayashi*>(h), false); if (app) { app->update(); app->draw(); } }
+// colours the viewer currently holds, 3 per object
+void ref_gui_colors(void* h, ref_real* rgb) {
+    DX12App* app = gui_of(static_cast<Kobayashi*>(h), false);
+    if (!app) return;
+    for (size_t i = 0; i < app->_constantBuffer.size(); ++i) {
+        rgb[3 * i + 0] = app->_constantBuffer[i].color.x; rgb[3 * i + 1] = app->_constantBuffer[i].color.y; rgb[3 * i + 2] = app->_constantBuffer[i].color.z;
+    }
+}
+// out[0] playing, out[1] _simFrame, out[2..10] slider values (float members), out[11..19] slider integer positions
+void ref_gui_state(void* h, double* out) {
+    Kobayashi* k = static_cast<Kobayashi*>(h);
+    out[0] = k->_updateFlag ? 1.0 : 0.0;
+    out[1] = (double)k->_simFrame;
+    for (int i = 0; i < 9; ++i) { out[2 + i] = (double)k->_crystalParameter[i].param_f.value; out[11 + i] = (double)k->_crystalParameter[i].param_i.value; }
+}
+
 }  // extern "C"

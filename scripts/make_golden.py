@@ -41,6 +41,21 @@ def run(name, nx, ny, steps, prec=32, nuclei=None, **params):
     print(name, {s: float(out[f'phi_{s}'].astype(np.float64).sum()) for s in steps})
 
 
+def run_colors(name, n):
+    """The viewer's per-object colours (iUpdateConstantBuffer, src/Kobayashi.cpp:309-345) for a designed phi field:
+    random values over [-0.05, 1.05] plus the ramp's break points, on a square grid (the reference derives the
+    object -> cell mapping from sqrt(#objects), :311-313)."""
+    r = po.Reference(n, n, 1e-4, prec=32)
+    rng = np.random.default_rng(20260101)
+    phi = (rng.random((n, n)) * 1.1 - 0.05).astype(np.float32)
+    phi[0, :8] = [0.0, 0.9, 0.99, 1.0, np.nextafter(np.float32(0.9), np.float32(1)), np.nextafter(np.float32(0.99), np.float32(1)), 0.45, 0.995]
+    z = np.zeros((n, n), np.float32)
+    r.set_fields(phi, z, z)
+    rgb = r.colors()                                    # object i -> colour, i = 0 .. n*n-1
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), n=n, phi=phi, rgb=rgb)
+    print(name, rgb.shape, float(rgb.astype(np.float64).sum()))
+
+
 if __name__ == "__main__":
     assert po.ref_available(32) and po.ref_available(64), "needs /root/reference (authoring container)"
     os.makedirs(OUT, exist_ok=True)
@@ -57,3 +72,4 @@ if __name__ == "__main__":
     # warm checkpoints for the tolerance windows of SURVEY §4 (G1/G2): state at step 500 and +1/+100/+200
     run("ref_f32_n128_j6_warm", 128, 128, [500, 501, 600, 700])
     run("ref_f64_n128_j6_warm", 128, 128, [500, 501, 1000], prec=64)
+    run_colors("ref_colors_n48", 48)

@@ -39,32 +39,76 @@ def test_isimulation_adapter_compiles_against_the_plugin_interface():
     assert r.returncode == 0, r.stdout
 
 
+def _run_reference_script(po, n, ops):
+    """The script of tests/cpp/adapter_check.cpp through the UNMODIFIED reference class (oracle/_ref): returns the dumps."""
+    ref = po.Reference(n, n, 1e-4, prec=32)
+    ref.gui_attach()
+    dumps = []
+    for op in ops:
+        if op == "f":
+            ref.gui_frame()
+        elif op[0] == "c":
+            ref.gui_command(int(op[1:]))
+        elif op[0] == "s":
+            i, c, p_ = (int(v) for v in op[1:].split(","))
+            ref.gui_hscroll(i, c, p_)
+        elif op == "n":
+            ref.add_nucleus(n // 4, n // 2 + 5)
+        elif op == "d":
+            dumps.append((ref.gui_state(), ref.gui_colors().astype("float64")))
+    return dumps
+
+
+# frames while playing; delta slider right (write + reset, and the reset's refresh already runs one iUpdate); pause;
+# frames do nothing; Next step x2; anisotropy thumb to 4 (reset while paused: no update); Next step; tau to its lower stop and
+# one more (ignored); Stop; Reset (defaults back); Play; an off-centre nucleus; frames.  SB_*: 0 line left, 1 line right, 5 thumb.
+ADAPTER_SCRIPT = ["f", "f", "d", "s4,1,0", "d", "c10", "f", "d", "c12", "c12", "d", "s5,5,4", "d", "c12", "d",
+                  "s0,0,0", "s0,0,0", "s0,0,0", "d", "c11", "d", "c9", "d", "c10", "n", "f", "d"]
+
+
 @pytest.mark.gpu
-def test_isimulation_adapter_shows_the_reference_picture(tmp_path):
-    """Per frame the viewer calls iUpdate then iUpdateConstantBuffer(cb, i) for every object; object i must get the
-    colour the reference gives it: the ramp of src/Kobayashi.cpp:318-342 applied to phi at the TRANSPOSED cell
-    (x, y) = (i / n, i % n) (:312-315)."""
+@pytest.mark.parametrize("kernel", ["fast", "strict"])
+def test_isimulation_adapter_behaves_like_the_reference_class(tmp_path, kernel):
+    """the plugin adapter against the reference class itself, both driven by the same viewer loop and the
+    same control-panel messages (src/Kobayashi.cpp:507-618: sliders write + reset, Reset, Play/Pause, Stop, Next step;
+    :241-249 reset-then-refresh-then-zero-counters; :309-345 colours with the transposed object -> cell mapping).
+    State (playing, _simFrame, the nine float parameters and thumb positions) must be EQUAL at every dump; colours equal to
+    8-bit quantisation plus the FP32 rounding chaos of a young nucleus (a few 1e-2 at the centre cell after
+    7+ cold sub-steps), which a wrong parameter, a missed reset or a missed update would exceed by far."""
     import numpy as np
-    import crystalgrowth_b200 as cg
+    from oracle import pyoracle as po
+    if not po.ref_available(32):
+        pytest.skip("oracle/_ref (the reference TU compiled in place) is not available")
+    n = 48
     exe = str(tmp_path / "adapter_check")
     pkg = os.path.join(ROOT, "crystalgrowth_b200")
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", HARNESS, "-I", os.path.join(ROOT, "include"), "-o", exe, ADAPTER_SRC,
                         "-L", pkg, "-lkobayashi_cuda", f"-Wl,-rpath,{pkg}"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
-    n, frames = 48, 3
-    r = subprocess.run([exe, str(n), str(frames)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    r = subprocess.run([exe, str(n), kernel] + ADAPTER_SCRIPT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=180)
     assert r.returncode == 0, r.stderr
-    got = np.array([[int(v) for v in line.split()] for line in r.stdout.strip().splitlines()], np.int32).reshape(n, n, 3)
-    g = cg.Kobayashi(n, n, 1e-4, kernel="fast")
-    g.add_nucleus(n // 4, n // 2 + 5)
-    for _ in range(frames):
-        g.iUpdate()
-    img = g.render_rgba()[..., :3].astype(np.int32)          # [y, x]
-    i = np.arange(n * n)
-    want = img[i % n, i // n].reshape(n, n, 3)               # object i -> cell (x, y) = (i / n, i % n)
-    assert np.abs(got - want).max() <= 1
-    assert np.abs(got - want.transpose(1, 0, 2)).max() > 50  # and the mapping matters for this picture
-    assert got.max() > 100                                   # the crystal is on the picture
+    lines = r.stdout.strip().splitlines()
+    want = _run_reference_script(po, n, ADAPTER_SCRIPT)
+    assert len(lines) == len(want) * (1 + n * n)
+    seen_pictures = []
+    for k, (state, colors) in enumerate(want):
+        blk = lines[k * (1 + n * n):(k + 1) * (1 + n * n)]
+        head = blk[0].split()
+        assert head[0] == "state"
+        assert bool(int(head[1])) == state["playing"], f"dump {k}: playing"
+        assert int(head[2]) == state["sim_frame"], f"dump {k}: _simFrame {head[2]} vs {state['sim_frame']}"
+        vals = np.array([float(v) for v in head[3:12]], np.float32)
+        assert np.array_equal(vals, state["values"].astype(np.float32)), f"dump {k}: parameters {vals} vs {state['values']}"
+        assert [int(v) for v in head[12:21]] == list(state["positions"]), f"dump {k}: thumb positions"
+        got = np.array([[float(v) for v in ln.split()] for ln in blk[1:]], np.float64)
+        d = np.abs(got - colors)
+        assert d.max() <= 0.04 and d.mean() <= 1e-3, f"dump {k}: colours differ, max {d.max()} mean {d.mean()}"
+        seen_pictures.append(colors)
+    # the script really moves the picture: after two frames the crystal is visible, Stop while paused shows the bare seed,
+    # and the last picture (extra off-centre nucleus) is not symmetric under transposition
+    assert seen_pictures[0].max() > 0.4
+    last = seen_pictures[-1].reshape(n, n, 3)
+    assert np.abs(last - last.transpose(1, 0, 2)).max() > 0.2
 
 
 @pytest.mark.gpu

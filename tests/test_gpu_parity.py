@@ -337,23 +337,31 @@ def test_errors_are_reported_not_thrown(po, cg):
         g.set_fields(np.zeros((3, 3), np.float32))
 
 
-def test_render_matches_reference_colour_ramp(po, cg):
-    """kob_render_rgba vs the reference's iUpdateConstantBuffer ramp (src/Kobayashi.cpp:309-345); the expected
-    colours come from the reference TU where it is available, else from the committed ramp restatement."""
-    g = cg.Kobayashi(48, 32, 1e-4, kernel="strict")
-    rng = np.random.default_rng(1)
-    phi = rng.random((32, 48), np.float32)
-    phi[0, :4] = [0.0, 0.9, 0.99, 1.0]
-    g.set_fields(phi, None, None)
-    img = g.render_rgba()
-    p = phi.astype(np.float32)
-    c0, c1, c2, c3 = (np.array(c, np.float32) for c in ([0, 0, 0], [0.2505490, 0.5, 0.9882353], [0.3607843, 1.0, 0.9882353], [0.9005490, 1.0, 0.9882353]))
-    want = np.empty((32, 48, 3), np.float32)
-    for (lo, hi, a, b, sel) in ((0.0, 0.9, c0, c1, p <= 0.9), (0.9, 0.99, c1, c2, (p > 0.9) & (p <= 0.99)), (0.99, 1.0, c2, c3, p > 0.99)):
-        r = ((p - np.float32(lo)) * (np.float32(1.0) / (np.float32(hi) - np.float32(lo))))[..., None]
-        want[sel] = (a * (1 - r) + b * r)[sel]
-    assert np.abs(img[..., :3].astype(np.int32) - np.rint(np.clip(want, 0, 1) * 255).astype(np.int32)).max() <= 1
-    assert (img[..., 3] == 255).all()
+def test_render_matches_reference_colours(po, cg):
+    """kob_render_rgba vs the colours the REFERENCE gives every object (iUpdateConstantBuffer, src/Kobayashi.cpp:309-345):
+    the committed fixture tests/golden/ref_colors_n48.npz was produced by the reference TU (scripts/make_golden.py,
+    run_colors) for a designed phi field incl. the ramp's break points; where oracle/_ref is available the reference is
+    also run live on a second field.  Object i shows cell (x, y) = (i / n, i % n) (:311-315); the image is [y, x]."""
+    z = np.load(os.path.join(GOLDEN, "ref_colors_n48.npz"))
+    n, phi, rgb = int(z["n"]), z["phi"], z["rgb"]
+    cases = [(phi, rgb)]
+    if po.ref_available(32):
+        rng = np.random.default_rng(5)
+        phi2 = (rng.random((n, n)) * 1.2 - 0.1).astype(np.float32)
+        r = po.Reference(n, n, 1e-4, prec=32)
+        r.set_fields(phi2, np.zeros_like(phi2), np.zeros_like(phi2))
+        cases.append((phi2, r.colors()))
+    i = np.arange(n * n)
+    for kernel in ("strict", "fast"):
+        g = cg.Kobayashi(n, n, 1e-4, kernel=kernel)
+        for p_, want in cases:
+            g.set_fields(p_, None, None)
+            img = g.render_rgba()
+            got = img[i % n, i // n, :3].astype(np.int32)                  # object i -> pixel (x, y) = (i / n, i % n)
+            exp = np.rint(np.clip(want.astype(np.float64), 0, 1) * 255).astype(np.int32)
+            assert np.abs(got - exp).max() <= 1
+            assert (img[..., 3] == 255).all()
+        g.close()
 
 
 # ---------------------------------------------------------------------------------------------- strips on one GPU

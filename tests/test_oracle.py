@@ -35,7 +35,7 @@ def _oracle_from(po, z, math=None, **kw):
     return o
 
 
-GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "ref_*.npz")))
+GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "ref_f*.npz")))      # field trajectories (ref_colors_* is the colour fixture)
 
 
 def test_golden_files_present():
@@ -245,3 +245,25 @@ def test_far_field_stays_exactly_zero(po):
     o.step(20)
     phi, t, th = o.fields()
     assert (phi[:8] == 0).all() and (t[:4] == 0).all() and (th[:8] == 0).all()
+
+
+def test_colour_fixture_is_the_reference_ramp(po):
+    """tests/golden/ref_colors_n48.npz (reference output, scripts/make_golden.py) against the ramp as the product restates
+    it (src/Kobayashi.cpp:318-342: three linear segments with breaks at 0.9 and 0.99, transposed object -> cell mapping)
+    — and, where oracle/_ref exists, against the reference TU run live on the same field."""
+    z = np.load(os.path.join(GOLDEN, "ref_colors_n48.npz"))
+    n, phi, rgb = int(z["n"]), z["phi"], z["rgb"]
+    c0, c1, c2, c3 = (np.array(c, np.float32) for c in ([0, 0, 0], [0.2505490, 0.5, 0.9882353], [0.3607843, 1.0, 0.9882353], [0.9005490, 1.0, 0.9882353]))
+    i = np.arange(n * n)
+    p_ = phi[i % n, i // n]                                        # object i reads _phi[_INDEX(i / n, i % n)]
+    want = np.empty((n * n, 3), np.float32)
+    one = np.float32(1.0)
+    for (lo, hi, a, b, sel) in ((0.0, 0.9, c0, c1, p_ <= np.float32(0.9)), (0.9, 0.99, c1, c2, (p_ > np.float32(0.9)) & (p_ <= np.float32(0.99))),
+                                (0.99, 1.0, c2, c3, p_ > np.float32(0.99))):
+        r = ((p_ - np.float32(lo)) * (one / (np.float32(hi) - np.float32(lo))))[:, None]
+        want[sel] = (a * (one - r) + b * r)[sel]
+    assert np.abs(want.astype(np.float64) - rgb.astype(np.float64)).max() <= 2e-6
+    if po.ref_available(32):
+        r = po.Reference(n, n, 1e-4, prec=32)
+        r.set_fields(phi, np.zeros_like(phi), np.zeros_like(phi))
+        assert np.array_equal(r.colors(), rgb)
