@@ -51,6 +51,10 @@ SIGNATURES = {
     "kob_sync": (C.c_int, [_P]),
     "kob_get_fields": (C.c_int, [_P, _P, _P, _P]),
     "kob_set_fields": (C.c_int, [_P, _P, _P, _P]),
+    "kob_get_fields_async": (C.c_int, [_P, _P, _P, _P]),
+    "kob_wait_fields": (C.c_int, [_P]),
+    "kob_get_window": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
+    "kob_set_window": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "kob_set_noise_field": (C.c_int, [_P, _P]),
     "kob_set_step_counter": (C.c_int, [_P, C.c_uint64]),
     "kob_get_step_counter": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -67,10 +71,12 @@ SIGNATURES = {
     "kob_abi_version": (C.c_int, []),
     "kob_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "kob_host_free": (C.c_int, [_P]),
+    "kob_host_alloc_near": (C.c_int, [_P, C.POINTER(_P), C.c_size_t]),
     "kob_ipc_export": (C.c_int, [_P, C.POINTER(KobIpcHandle)]),
     "kob_ipc_link": (C.c_int, [_P, C.POINTER(KobIpcHandle), C.POINTER(KobIpcHandle)]),
     "kob_link_local": (C.c_int, [_P, _P, _P]),
     "kob_halo_refresh": (C.c_int, [_P]),
+    "kob_ring_join": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32]),
 }
 
 _lib = None

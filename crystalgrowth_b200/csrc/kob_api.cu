@@ -3,7 +3,15 @@
 // There is NO CPU fallback: every entry point that needs the device fails with KOB_ERR_NO_DEVICE /
 // KOB_ERR_CUDA when it is missing.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
+#include <chrono>
+#include <thread>
+
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +80,15 @@ constexpr uint32_t IPC_MAGIC = 0x4b4f4231u;  // "KOB1"
 
 }  // namespace
 
+// Shared-memory segment of one ring (kob_ring_join): per strip a round counter and the density probe of the last two rounds.
+struct RingShm {
+    uint32_t magic, world;
+    struct Slot { volatile uint64_t round; volatile double frac[2]; char pad[40]; } slot[64];
+};
+constexpr uint32_t RING_MAGIC = 0x4b52494eu;   // "KRIN"
+constexpr int RING_PERIOD = 64;                // sub-steps between agreements
+constexpr double RING_TO_SINGLE = 0.04, RING_TO_PAIRS = 0.03;
+
 struct kob_ctx {
     int64_t nx = 0, ny = 0, ny_global = 0, y0 = 0;
     int prec = KOB_F32, kernel = KOB_KERNEL_FAST, device = 0;
@@ -86,13 +103,19 @@ struct kob_ctx {
     uint8_t* rgba = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // asynchronous readback (kob_get_fields_async): device snapshot + second stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    char* snap = nullptr;             // 3 x nx*ny elements, unpadded
+    bool copy_pending = false;
     Neighbour lower, upper;
     bool linked = false;
     uint64_t launches = 0;
     // FAST kernel: TMA descriptors of the four field buffers, job decomposition, job-counter bookkeeping
-    FastMaps maps{}, maps2{}, maps_far{};   // single-step boxes; two-step boxes (72 wide); far pass: phi 64 wide + T 72 wide
+    FastMapsIO maps_io{};         // single-step kernel: input boxes (phi, T 68 wide; theta 64 wide) and output boxes (60 wide)
+    FastMaps maps2{}, maps_far{};   // two-step boxes (72 wide); far pass: phi 64 wide + T 72 wide
     int fast_yj = 64, fast_yj_b = 32;
-    int fast_dense = 1;           // straight-line dense tier of the single-step kernel: 0 off, 1 predicted, 2 always (test knob)
+    int fast_free = 1;            // a CTA that met data-dependent work switches to per-warp job claims (0: never; test knob)
     int nsm = 0;                  // SMs of the device
     std::unordered_map<const void*, int> occ;   // resident CTAs per SM of each kernel instantiation this context launched
     bool fast_yj_env = false, fast2_yj_env = false;   // job heights given explicitly: no automatic shortening
@@ -112,6 +135,11 @@ struct kob_ctx {
     double general_frac = 0.0;
     bool single_mode = false;          // adaptive policy: the field is dense, use the single-step kernel
     uint64_t n_single = 0, n_paired = 0;
+    // ring-wide step-path agreement (kob_ring_join): shared segment, this strip's slot, sub-steps since the join
+    struct RingShm* ring = nullptr;
+    int ring_rank = 0, ring_world = 0, ring_mode = 1;    // mode: 1 = two-step pairs (sparse field), 0 = single-step kernel
+    uint64_t ring_steps = 0, ring_round = 0;
+    std::string ring_name;
     int fast2_yj = 96, fast2_yj_b = 32, fast2_lock = 0, fast2_far = 1, fast2_far_cta = 1;
     int* worklist = nullptr;      // far/general launch pair: [count, claim, -, -, job ids ...]
     long long worklist_cap = 0;
@@ -189,7 +217,7 @@ StepArgs<real> args_of(kob_ctx* c) {
     a.ticket = reinterpret_cast<unsigned int*>(c->base + c->L.off_ticket);
     a.pitch = c->L.pitch; a.nx = (int)c->nx; a.ny = (int)c->ny; a.y0 = c->y0;
     a.nfbx = c->L.nfbx; a.nfby = c->L.nfby;
-    a.cur = c->cur; a.linked = c->linked ? 1 : 0; a.epoch = c->epoch;
+    a.cur = c->cur; a.tcur = c->tcur; a.linked = c->linked ? 1 : 0; a.epoch = c->epoch;
     return a;
 }
 
@@ -205,31 +233,28 @@ int build_fast_maps(kob_ctx* c) {
         q != cudaDriverEntryPointSuccess)
         return fail(c, KOB_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from this driver");
     EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
-    const int bw = FastGeom::BW;
     const cuuint64_t dims[2] = {(cuuint64_t)c->L.pitch, (cuuint64_t)c->L.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)c->L.pitch * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)FAST_RB};
     const cuuint32_t estr[2] = {1, 1};
-    CUtensorMap* maps[4] = {&c->maps.phi[0], &c->maps.phi[1], &c->maps.t[0], &c->maps.t[1]};
-    const size_t offs[4] = {c->L.off_phi[0], c->L.off_phi[1], c->L.off_t[0], c->L.off_t[1]};
-    const cuuint32_t box2[2] = {(cuuint32_t)F2_BW, (cuuint32_t)FAST_RB};       // the two-step kernel's wider box
-    CUtensorMap* maps2[4] = {&c->maps2.phi[0], &c->maps2.phi[1], &c->maps2.t[0], &c->maps2.t[1]};
-    for (int i = 0; i < 4; ++i) {
-        CUresult r = enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r == CUDA_SUCCESS)
-            r = enc(maps2[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box2, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    auto encode = [&](CUtensorMap* m, size_t off, int box_w) -> int {
+        const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)FAST_RB};
+        const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-    }
-    const cuuint32_t box3[2] = {(cuuint32_t)FAR2_PBW, (cuuint32_t)FAST_RB};
+        return KOB_OK;
+    };
     for (int i = 0; i < 2; ++i) {
-        CUresult r = enc(&c->maps_far.phi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->base + offs[i], dims, strides, box3, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(c, KOB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        // single-step kernel: 68-wide phi / T / theta input boxes, 60-wide output boxes
+        KOB_TRY(encode(&c->maps_io.phi_in[i], c->L.off_phi[i], FastGeom::BW));
+        KOB_TRY(encode(&c->maps_io.t_in[i], c->L.off_t[i], FastGeom::BW));
+        KOB_TRY(encode(&c->maps_io.th_in[i], c->L.off_theta[i], FastGeom::BW));
+        KOB_TRY(encode(&c->maps_io.phi_out[i], c->L.off_phi[i], FastGeom::OUTC));
+        KOB_TRY(encode(&c->maps_io.t_out[i], c->L.off_t[i], FastGeom::OUTC));
+        KOB_TRY(encode(&c->maps_io.th_out[i], c->L.off_theta[i], FastGeom::OUTC));
+        // two-step kernel: 72-wide boxes; its far pass: phi 64 wide (only looked at), T 72 wide
+        KOB_TRY(encode(&c->maps2.phi[i], c->L.off_phi[i], F2_BW));
+        KOB_TRY(encode(&c->maps2.t[i], c->L.off_t[i], F2_BW));
+        KOB_TRY(encode(&c->maps_far.phi[i], c->L.off_phi[i], FAR2_PBW));
         c->maps_far.t[i] = c->maps2.t[i];
     }
     return KOB_OK;
@@ -252,16 +277,17 @@ int kernel_occupancy(kob_ctx* c, const void* kern, int threads, int smem, int* o
     return KOB_OK;
 }
 
-// Rows per job: the configured height or a shorter one (halvings down to 4) — whichever minimises the serial work of the
-// busiest warp, rounds x (rows + warm-up rows).  On big grids that is the configured height; on small ones the jobs shrink
-// until every warp of the persistent grid has one.  Not applied when the height was set explicitly (environment).
+// Rows per job: the configured height or a shorter one (halvings down to 4) — whichever minimises the expected makespan of the
+// dynamically scheduled queue, (total rows incl. warm-up rows) / warps + one job (the last one to finish).  On big grids that is
+// the configured height; on small ones the jobs shrink until the tail is short and every warp of the persistent grid has work.
+// Not applied when the height was set explicitly (environment).  Bit-neutral, like every job knob.
 int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps, int warm) {
     if (fixed) return yj;
     int best = yj;
-    long long best_cost = -1;
+    double best_cost = -1.0;
     for (int h = yj; h >= 4; h /= 2) {
         const long long jobs = (long long)nstrips * ((ny + h - 1) / h);
-        const long long cost = ((jobs + warps - 1) / warps) * (h + warm);
+        const double cost = (double)jobs * (h + warm) / (double)warps + (double)(h + warm);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = h; }
     }
     return std::max(4, best / 4 * 4);
@@ -270,7 +296,7 @@ int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps
 template <int JM, int NOISE, bool ROT>
 int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     auto kern = kob_step_fast<JM, NOISE, ROT>;
-    const int smem = FAST_WARPS * FAST_WARP_BYTES + FAST_WARPS * FAST_NST * 8;
+    const int smem = fast_smem_bytes(FAST_WARPS);
     int cps = 0;
     KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kern), FAST_WARPS * 32, smem, &cps));
     const int nsm = c->nsm;
@@ -286,7 +312,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     f.nseg = f.nseg_a + (int)((rest + f.yj_b - 1) / f.yj_b);
     f.cta_jobs = f.nstrips < FAST_WARPS ? 0 : c->fast_cta_jobs;   // narrow grids: a CTA job would be mostly padding warps
     f.no_skip = c->fast_no_skip;
-    f.dense_mode = c->fast_dense;
+    f.free_mode = c->fast_free;
     f.nstrips_p = (f.nstrips + FAST_WARPS - 1) / FAST_WARPS * FAST_WARPS;
     // linked strips: how many jobs touch the low / high seam (the kernel publishes a side when its jobs are done)
     f.seam_jobs[0] = f.seam_jobs[1] = 0;
@@ -306,7 +332,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         KOB_CUDA(c, cudaMemsetAsync(live_ctr, 0, sizeof(unsigned int), c->stream));
         f.live_ctr = live_ctr;
     }
-    kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps, a, f);
+    kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps_io, a, f);
     if (probe) {
         KOB_CUDA(c, cudaMemcpyAsync(c->h_count, live_ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
         KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
@@ -325,10 +351,16 @@ FastArgs fast_args_of(kob_ctx* c, const StepArgs<float>& a) {
     ColdK& K = f.ck;
     K.e = REF_DEADBAND;
     // re-assigned angle = quadrant offset + atan(w), w in [-1, 1] (kob_row.cuh): the reference's branch offsets
-    // 0 / PI_F / 2 PI_F (src/Kobayashi.cpp:160-167) with the +-pi/4 of the argument fold
+    // 0 / PI_F / 2 PI_F (src/Kobayashi.cpp:160-167) with the +-pi/4 of the argument fold, as a bilinear form in the signs
     const double q4 = 0.78539816339744830962, pif = (double)REF_PI_F;
-    K.off1 = (float)q4; K.off2 = (float)(pif - q4); K.off3 = (float)(pif + q4); K.off4 = (float)(2.0 * pif - q4);
+    K.off_c = REF_PI_F; K.off_y = -0.5f * REF_PI_F; K.off_s = (float)(q4 - 0.5 * pif);
     K.half_pi = 0.5f * REF_PI_F;
+    {   // case A cells: cos / sin (j * angl) with angl = +-0.5f * PI_F, float arithmetic like the reference (:156-158, :170-171)
+        volatile float ap = P.aniso * (0.5f * REF_PI_F - P.theta0), am = P.aniso * (-0.5f * REF_PI_F - P.theta0);
+        K.cfl_p = std::cos((float)ap); K.sfl_p = std::sin((float)ap); K.cfl_m = std::cos((float)am); K.sfl_m = std::sin((float)am);
+        K.j_rev = (float)((double)P.aniso / 6.283185307179586);
+        K.jth0_rev = (float)(-(double)P.aniso * (double)P.theta0 / 6.283185307179586);
+    }
     // eps, eps' of a cell that holds theta = 0 (far field), evaluated like src/Kobayashi.cpp:170-171
     const double arg0 = (double)P.aniso * (0.0 - (double)P.theta0);
     volatile float c0 = (float)std::cos(arg0), s0 = (float)std::sin(arg0);
@@ -379,6 +411,15 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     f.cta_jobs = c->fast2_lock;
     f.no_skip = c->fast_no_skip;
     f.nstrips_p = (f.nstrips + F2_WARPS - 1) / F2_WARPS * F2_WARPS;
+    // linked strips: row ranges (F2_RANGES per job) of the jobs that touch the low / high seam — a side is published as soon
+    // as they are done, by whichever pass of the launch pair completes the last one
+    f.seam_jobs[0] = f.seam_jobs[1] = 0;
+    for (int seg = 0; seg < f.nseg; ++seg) {
+        const long long y0 = seg < f.nseg_a ? (long long)seg * f.yj : (long long)f.nseg_a * f.yj + (long long)(seg - f.nseg_a) * f.yj_b;
+        const long long y1 = std::min<long long>(y0 + (seg < f.nseg_a ? f.yj : f.yj_b), c->ny);
+        if (y0 < GY + 2) f.seam_jobs[0] += (unsigned)(F2_RANGES * f.nstrips);
+        if (y1 > c->ny - GY - 1) f.seam_jobs[1] += (unsigned)(F2_RANGES * f.nstrips);
+    }
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     if (c->fast2_far && !f.cta_jobs) {
         // far/general launch pair: the light far pass visits every job and leaves the rest on the work list
@@ -441,7 +482,7 @@ int launch_two_steps_fast(kob_ctx* c) {
 #undef KOB_FAST2_CASE
     KOB_CUDA(c, cudaGetLastError());
     c->launches += 1;
-    c->cur ^= 1; c->tcur ^= 1; c->step += 2; c->epoch += 1;
+    c->cur ^= 1; c->tcur ^= 1; c->step += 2; c->epoch += 2;
     return KOB_OK;
 }
 
@@ -622,7 +663,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     c->upper.base = c->base; c->upper.ny = ny;
     if (c->kernel == KOB_KERNEL_FAST) {
         // tuning knobs (defaults are the measured best): cells per lane = 2*NP, rows per job
-        if (const char* e_ = std::getenv("KOB_FAST_DENSE")) c->fast_dense = std::min(2, std::max(0, std::atoi(e_)));
+        if (const char* e_ = std::getenv("KOB_FAST_FREE")) c->fast_free = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST_YJ")) { c->fast_yj = c->fast_yj_b = std::max(4, std::atoi(e_)); c->fast_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST_CTA")) c->fast_cta_jobs = std::min(2, std::max(0, std::atoi(e_)));
         if (const char* e_ = std::getenv("KOB_FAST_NOSKIP")) c->fast_no_skip = std::atoi(e_) ? 1 : 0;
@@ -650,6 +691,14 @@ int kob_destroy(kob_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->lower.ipc && c->lower.base) cudaIpcCloseMemHandle(c->lower.base);
     if (c->upper.ipc && c->upper.base && c->upper.base != c->lower.base) cudaIpcCloseMemHandle(c->upper.base);
+    if (c->ring) {
+        munmap(c->ring, sizeof(RingShm));
+        if (c->ring_rank == 0) shm_unlink(c->ring_name.c_str());
+    }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->snap) cudaFree(c->snap);
     if (c->noise_field) cudaFree(c->noise_field);
     if (c->rgba) cudaFree(c->rgba);
     if (c->worklist) cudaFree(c->worklist);
@@ -712,22 +761,60 @@ void poll_density_probe(kob_ctx* c) {
     }
 }
 
+// Ring-wide agreement on the step path (every RING_PERIOD sub-steps since kob_ring_join): publish this strip's density probe,
+// wait for every strip's, take the maximum, apply the hysteresis.  Every strip computes the same decision from the same numbers.
+static int ring_agree(kob_ctx* c) {
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));          // the asynchronous density probe has landed
+    poll_density_probe(c);
+    RingShm* R = c->ring;
+    const uint64_t k = ++c->ring_round;
+    R->slot[c->ring_rank].frac[k & 1] = c->general_frac;
+    __sync_synchronize();
+    R->slot[c->ring_rank].round = k;
+    const auto t0 = std::chrono::steady_clock::now();
+    double m = 0.0;
+    for (int r = 0; r < c->ring_world; ++r) {
+        while (R->slot[r].round < k) {
+            std::this_thread::yield();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60))
+                return fail(c, KOB_ERR_STATE, "kob_ring_join: a strip of the ring did not reach the step-path agreement within 60 s "
+                                              "(all strips must be stepped by the same amounts)");
+        }
+        __sync_synchronize();
+        m = std::max(m, (double)R->slot[r].frac[k & 1]);
+    }
+    if (c->ring_mode == 1 && m > RING_TO_SINGLE) c->ring_mode = 0;
+    else if (c->ring_mode == 0 && m < RING_TO_PAIRS) c->ring_mode = 1;
+    c->single_mode = c->ring_mode == 0;                     // single-step launches probe the live-job fraction
+    return KOB_OK;
+}
+
 int kob_step(kob_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return KOB_ERR_INVALID_ARG;
     KOB_TRY(set_device(c));
+    const bool ring = c->ring != nullptr && c->linked && c->fast2 == 2 && c->kernel == KOB_KERNEL_FAST;
     for (int64_t s = 0; s < nsteps;) {
         poll_density_probe(c);
         // KOB_FAST2 / kob_set_path_mode: 0 = single-step kernel, 1 = pairs, 2 = adaptive.  Linked strips must all run the same
-        // launch sequence, so "adaptive" means pairs there unless the caller (StripRing) agrees on a mode across the ring
-        // and sets it on every strip.
-        const bool want_single = c->fast2 == 0 || (c->fast2 == 2 && !c->linked && c->single_mode);
-        if (nsteps - s >= 2 && fast2_eligible(c) && !want_single) {
+        // launch sequence: "adaptive" there means pairs, unless the ring agrees on a mode — through kob_ring_join (below), or
+        // by the caller setting the same mode on every strip at the same step.
+        bool want_single = c->fast2 == 0 || (c->fast2 == 2 && !c->linked && c->single_mode);
+        int64_t left = nsteps - s;
+        if (ring) {
+            if (c->ring_steps > 0 && c->ring_steps % RING_PERIOD == 0 && c->ring_round < c->ring_steps / RING_PERIOD) KOB_TRY(ring_agree(c));
+            want_single = c->ring_mode == 0;
+            left = std::min<int64_t>(left, RING_PERIOD - (int64_t)(c->ring_steps % RING_PERIOD));   // pairs never straddle an agreement
+        }
+        int done = 1;
+        if (left >= 2 && fast2_eligible(c) && !want_single) {
             KOB_TRY(launch_two_steps_fast(c));                  // temporal blocking: two sub-steps per launch pair
-            s += 2; c->n_paired += 2;
+            done = 2; c->n_paired += 2;
         } else {
             KOB_TRY(KOB_DISPATCH(c, launch_one_step, c));
-            s += 1; c->n_single += 1;
+            c->n_single += 1;
         }
+        s += done;
+        if (ring) c->ring_steps += (uint64_t)done;
     }
     return KOB_OK;
 }
@@ -750,15 +837,28 @@ int kob_update(kob_ctx* c) {
     return KOB_OK;
 }
 
-// Linked strips: did an edge tile give up waiting for a neighbour (kob_common.cuh, wait_flag)?
+// Linked strips: did an edge tile give up waiting for a neighbour, or see it run another launch sequence (kob_common.cuh, wait_flag)?
+static int fault_status(kob_ctx* c, uint32_t fault) {
+    if (fault == 0) return KOB_OK;
+    return fail(c, KOB_ERR_STATE, fault == 2 ? "a neighbour strip runs a different launch sequence (single steps vs two-step pairs): "
+                                               "set the same path mode on every strip of the ring; fields are invalid"
+                                             : "a neighbour strip did not reach the expected step within 20 s "
+                                               "(strips must be stepped together); fields are invalid");
+}
 static int check_fault(kob_ctx* c) {
     if (!c->linked) return KOB_OK;
     uint32_t fault = 0;
     KOB_CUDA(c, cudaMemcpyAsync(&fault, c->base + c->L.off_arrive + 8, 4, cudaMemcpyDeviceToHost, c->stream));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (fault) return fail(c, KOB_ERR_STATE, "a neighbour strip did not reach the expected step within 20 s "
-                                             "(strips must be stepped together); fields are invalid");
-    return KOB_OK;
+    return fault_status(c, fault);
+}
+// After the copy stream has drained: look at the fault word without touching the compute stream's queue.
+static int check_fault_nosync(kob_ctx* c) {
+    if (!c->linked) return KOB_OK;
+    uint32_t fault = 0;
+    KOB_CUDA(c, cudaMemcpyAsync(&fault, c->base + c->L.off_arrive + 8, 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    return fault_status(c, fault);
 }
 
 int kob_sync(kob_ctx* c) {
@@ -798,8 +898,82 @@ int kob_set_fields(kob_ctx* c, const void* phi, const void* t, const void* angl)
     return KOB_OK;
 }
 
+int kob_get_fields_async(kob_ctx* c, void* phi, void* t, void* angl) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    const size_t e = c->L.elem, w = (size_t)c->nx * e, sp = (size_t)c->L.pitch * e, n = w * (size_t)c->ny;
+    const size_t o = ((size_t)GY * c->L.pitch + GX) * e;
+    if (!c->copy_stream) {
+        KOB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        KOB_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        KOB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+        KOB_CUDA(c, cudaMalloc((void**)&c->snap, 3 * n));
+    }
+    if (c->copy_pending) KOB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));     // the snapshot buffer is free again
+    // snapshot (padded -> packed) on the compute stream: the following steps may overwrite the ping-pong buffers at once
+    if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(c->snap, w, c->base + c->L.off_phi[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToDevice, c->stream));
+    if (t) KOB_CUDA(c, cudaMemcpy2DAsync(c->snap + n, w, c->base + c->L.off_t[c->cur] + o, sp, w, c->ny, cudaMemcpyDeviceToDevice, c->stream));
+    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(c->snap + 2 * n, w, c->base + c->L.off_theta[c->tcur] + o, sp, w, c->ny, cudaMemcpyDeviceToDevice, c->stream));
+    KOB_CUDA(c, cudaEventRecord(c->ev_snap, c->stream));
+    KOB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    if (phi) KOB_CUDA(c, cudaMemcpyAsync(phi, c->snap, n, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (t) KOB_CUDA(c, cudaMemcpyAsync(t, c->snap + n, n, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (angl) KOB_CUDA(c, cudaMemcpyAsync(angl, c->snap + 2 * n, n, cudaMemcpyDeviceToHost, c->copy_stream));
+    KOB_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+    c->copy_pending = true;
+    return KOB_OK;
+}
+
+int kob_wait_fields(kob_ctx* c) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    if (!c->copy_pending) return KOB_OK;
+    KOB_TRY(set_device(c));
+    KOB_CUDA(c, cudaEventSynchronize(c->ev_copied));
+    c->copy_pending = false;
+    return check_fault_nosync(c);
+}
+
+static bool window_ok(const kob_ctx* c, int64_t x0, int64_t y0, int64_t w, int64_t h) {
+    return x0 >= 0 && y0 >= 0 && w > 0 && h > 0 && x0 + w <= c->nx && y0 + h <= c->ny;
+}
+
+int kob_get_window(kob_ctx* c, int64_t x0, int64_t y0, int64_t w, int64_t h, void* phi, void* t, void* angl) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    if (!window_ok(c, x0, y0, w, h)) return fail(c, KOB_ERR_INVALID_ARG, "window outside the strip");
+    KOB_TRY(set_device(c));
+    const size_t e = c->L.elem, wb = (size_t)w * e, sp = (size_t)c->L.pitch * e;
+    const size_t o = ((size_t)(GY + y0) * c->L.pitch + GX + (size_t)x0) * e;
+    if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(phi, wb, c->base + c->L.off_phi[c->cur] + o, sp, wb, h, cudaMemcpyDeviceToHost, c->stream));
+    if (t) KOB_CUDA(c, cudaMemcpy2DAsync(t, wb, c->base + c->L.off_t[c->cur] + o, sp, wb, h, cudaMemcpyDeviceToHost, c->stream));
+    if (angl) KOB_CUDA(c, cudaMemcpy2DAsync(angl, wb, c->base + c->L.off_theta[c->tcur] + o, sp, wb, h, cudaMemcpyDeviceToHost, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_fault(c);
+}
+
+int kob_set_window(kob_ctx* c, int64_t x0, int64_t y0, int64_t w, int64_t h, const void* phi, const void* t, const void* angl) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    if (!window_ok(c, x0, y0, w, h)) return fail(c, KOB_ERR_INVALID_ARG, "window outside the strip");
+    KOB_TRY(set_device(c));
+    const size_t e = c->L.elem, wb = (size_t)w * e, sp = (size_t)c->L.pitch * e;
+    const size_t o = ((size_t)(GY + y0) * c->L.pitch + GX + (size_t)x0) * e;
+    if (phi) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_phi[c->cur] + o, sp, phi, wb, wb, h, cudaMemcpyHostToDevice, c->stream));
+    if (t) KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_t[c->cur] + o, sp, t, wb, wb, h, cudaMemcpyHostToDevice, c->stream));
+    if (angl) {
+        KOB_CUDA(c, cudaMemcpy2DAsync(c->base + c->L.off_theta[c->tcur] + o, sp, angl, wb, wb, h, cudaMemcpyHostToDevice, c->stream));
+        // the two-step kernel only writes non-zero angles into the other buffer: the window must not hold stale ones there
+        KOB_CUDA(c, cudaMemset2DAsync(c->base + c->L.off_theta[c->tcur ^ 1] + o, sp, 0, wb, h, c->stream));
+    }
+    KOB_TRY(KOB_DISPATCH(c, refresh_impl, c));
+    if (angl) KOB_TRY(KOB_DISPATCH(c, rebuild_flags_impl, c));
+    return KOB_OK;
+}
+
 int kob_set_noise_field(kob_ctx* c, const float* r) {
     if (!c) return KOB_ERR_INVALID_ARG;
+    // a host-injected field rules the two-step path out on THIS strip only; inside a ring that would desynchronise the launch
+    // sequences, so the ring has to be in single-step mode (kob_set_path_mode(KOB_PATH_SINGLE) on every strip) first
+    if (r && c->linked && c->kernel == KOB_KERNEL_FAST && c->fast2 != 0)
+        return fail(c, KOB_ERR_STATE, "linked FAST strips: set KOB_PATH_SINGLE on every strip of the ring before injecting a noise field");
     KOB_TRY(set_device(c));
     if (!r) {
         if (c->noise_field) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->noise_field); c->noise_field = nullptr; }
@@ -868,6 +1042,51 @@ int kob_host_alloc(void** p, size_t bytes) {
 }
 int kob_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? KOB_OK : KOB_ERR_CUDA; }
 
+// CPUs of the NUMA node the device hangs off (sysfs), or an empty set.
+static bool cpus_near_device(int device, cpu_set_t* set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return false;
+    for (char* p = bus; *p; ++p) *p = (char)std::tolower((unsigned char)*p);
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* fp = std::fopen(path, "r");
+    int node = -1;
+    if (fp) { if (std::fscanf(fp, "%d", &node) != 1) node = -1; std::fclose(fp); }
+    if (node < 0) return false;
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    fp = std::fopen(path, "r");
+    if (!fp) return false;
+    CPU_ZERO(set);
+    int a = 0, b = 0, n = 0;
+    char sep = 0;
+    while (std::fscanf(fp, "%d", &a) == 1) {           // "0-31,64-95"
+        b = a;
+        int ch = std::fgetc(fp);
+        if (ch == '-') { if (std::fscanf(fp, "%d", &b) != 1) b = a; ch = std::fgetc(fp); }
+        for (int k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET(k, set); ++n; }
+        sep = (char)ch;
+        if (sep != ',') break;
+    }
+    std::fclose(fp);
+    return n > 0;
+}
+
+int kob_host_alloc_near(kob_ctx* c, void** p, size_t bytes) {
+    if (!c || !p) return KOB_ERR_INVALID_ARG;
+    cpu_set_t near_set, old_set;
+    const bool have = cpus_near_device(c->device, &near_set) && sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    bool moved = false;
+    if (have) {
+        cpu_set_t both;                                 // stay inside the CPUs this process is allowed to use
+        CPU_AND(&both, &near_set, &old_set);
+        if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    const int rc = kob_host_alloc(p, bytes);
+    if (rc == KOB_OK && moved) std::memset(*p, 0, bytes);   // first touch from a near CPU
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    return rc;
+}
+
 // ---- strips ------------------------------------------------------------------------------------------
 
 int kob_ipc_export(kob_ctx* c, kob_ipc_handle* out) {
@@ -887,6 +1106,10 @@ static int check_neighbour(kob_ctx* c, int64_t nx, int64_t ny, int64_t nyg, int6
     const int64_t expect = is_lower ? ((c->y0 - ny) % nyg + nyg) % nyg : (c->y0 + c->ny) % nyg;
     if (y0 != expect) return fail(c, KOB_ERR_INVALID_ARG, is_lower ? "lower neighbour is not adjacent (y0 mismatch)" : "upper neighbour is not adjacent (y0 mismatch)");
     if (ny < 2) return fail(c, KOB_ERR_INVALID_ARG, "neighbour strip too thin");
+    // every strip of a ring must run the same launch sequence; the FAST two-step path needs 8 rows, so a ring of FAST strips
+    // with a thinner member would have that member fall back to single steps alone
+    if (c->kernel == KOB_KERNEL_FAST && (ny < 8 || c->ny < 8))
+        return fail(c, KOB_ERR_INVALID_ARG, "linked FAST strips need at least 8 rows each (use the STRICT kernel for thinner strips)");
     return KOB_OK;
 }
 
@@ -929,6 +1152,23 @@ int kob_link_local(kob_ctx* c, kob_ctx* lower, kob_ctx* upper) {
     c->lower.base = lower->base; c->lower.ny = lower->ny; c->lower.ipc = false;
     c->upper.base = upper->base; c->upper.ny = upper->ny; c->upper.ipc = false;
     c->linked = true;
+    return KOB_OK;
+}
+
+int kob_ring_join(kob_ctx* c, const char* name, int32_t rank, int32_t world) {
+    if (!c || !name || world < 1 || world > 64 || rank < 0 || rank >= world || std::strlen(name) > 47) return KOB_ERR_INVALID_ARG;
+    if (c->ring) return fail(c, KOB_ERR_STATE, "strip already joined a ring");
+    c->ring_name = std::string("/kobring_") + name;
+    const int fd = shm_open(c->ring_name.c_str(), O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return fail(c, KOB_ERR_STATE, "shm_open(" + c->ring_name + ") failed");
+    if (ftruncate(fd, sizeof(RingShm)) != 0) { close(fd); return fail(c, KOB_ERR_STATE, "ftruncate on the ring segment failed"); }
+    void* p = mmap(nullptr, sizeof(RingShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(c, KOB_ERR_STATE, "mmap of the ring segment failed");
+    c->ring = static_cast<RingShm*>(p);                      // a fresh segment is zero-filled: every slot starts at round 0
+    c->ring->magic = RING_MAGIC; c->ring->world = (uint32_t)world;
+    c->ring_rank = rank; c->ring_world = world; c->ring_mode = 1; c->ring_steps = 0; c->ring_round = 0;
+    c->ring->slot[rank].round = 0;
     return KOB_OK;
 }
 

@@ -68,8 +68,9 @@ struct StepArgs {
     long long y0;              // global row of local row 0
     int nfbx, nfby;            // theta-flag blocks
     int cur;                   // buffer read by this step
+    int tcur;                  // which theta buffer `theta` is (the two-step kernel swaps them)
     int linked;                // 1: neighbours are other strips -> wait/signal through `arrive`
-    unsigned int epoch;        // number of steps this strip has completed before this launch
+    unsigned int epoch;        // number of SUB-STEPS this strip has completed before this launch
 };
 
 template <typename real>
@@ -158,26 +159,34 @@ constexpr unsigned long long WAIT_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000u
 
 // Bounded: a neighbour that never arrives (its process died, or strips were stepped out of order) raises the
 // strip's fault word instead of hanging the GPU; the host reports it from kob_sync / kob_get_fields.
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* fault) {
-    if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return;
-    const unsigned long long t0 = globaltimer_ns();
-    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-        __nanosleep(100);
-        if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { atomicExch(fault, 1u); return; }
+// `epoch` counts SUB-STEPS completed before this launch and `sub` the sub-steps this launch performs (1, or 2 for a two-step
+// launch pair).  A neighbour is never more than one launch ahead, so its flag reads epoch (not there yet) or epoch + sub;
+// anything else means the strips of the ring are not running the same launch sequence (one does pairs, the other single
+// steps): that is reported at once through the fault word instead of after a 20 s spin.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* fault, uint32_t sub = 0u) {
+    uint32_t v = ld_acquire_sys(flag);
+    if ((int)(v - epoch) < 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)((v = ld_acquire_sys(flag)) - epoch) < 0) {
+            __nanosleep(100);
+            if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { atomicExch(fault, 1u); return; }
+        }
     }
+    if (sub != 0u && v != epoch && v != epoch + sub) atomicExch(fault, 2u);
 }
 
 template <typename real>
 __device__ __forceinline__ void wait_neighbours(const StepArgs<real>& a, bool touches_low, bool touches_high) {
     if (!a.linked) return;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        if (touches_low) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
-        if (touches_high) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
+        if (touches_low) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2], 1u);
+        if (touches_high) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2], 1u);
     }
     __syncthreads();
 }
 
-// Last CTA of the grid publishes "this strip completed epoch+1 steps" into both neighbours.
+// Last CTA of the grid publishes "this strip completed epoch + 1 sub-steps" into both neighbours (STRICT kernel; the FAST
+// kernels publish each side as soon as the jobs touching it are done, kob_fast.cuh).
 template <typename real>
 __device__ __forceinline__ void signal_neighbours(const StepArgs<real>& a) {
     if (!a.linked) return;

@@ -21,10 +21,11 @@
 //     every alias (own ghost columns, neighbour strips' ghost rows — peer memory over NVLink when P > 1).
 //   * theta traffic is predicated: read only inside blocks flagged "theta may be non-zero", written only where the
 //     state machine re-assigns it.
-//   * three tiers per 4-row chunk: (1) far-field shortcut — phi rows (and the 4 rows before them) all +0: only T
-//     diffuses; (2) per-row vote — the data-dependent block runs for the rows that need it; (3) DENSE — when every row
-//     of the previous chunk needed it, the chunk runs as straight-line code without asking.  All three produce the same
-//     bits (the data-dependent block is valid for every cell; tiers only skip work that would produce +0 / constants).
+//   * two tiers per 4-row chunk: (1) far-field shortcut — phi rows (and the 4 rows before them) all +0: only T
+//     diffuses; (2) per-row vote — the data-dependent block runs for the rows that need it.  Same bits either way (the
+//     shortcut only skips work that would produce +0 / constants).
+//   * a CTA that met data-dependent work stops claiming CTA-wide jobs and lets every warp claim its own (no block-level
+//     barrier any more: in developed fields rows take unequal time and the barriers cost ~10 %).
 #ifndef KOB_FAST_CUH
 #define KOB_FAST_CUH
 
@@ -51,7 +52,7 @@ struct FastArgs {
     int cta_jobs;                  // 1/2: a CTA claims 8 adjacent strips of one segment; 1 = always in lock-step, 2 = adaptive
     int nstrips_p;                 // strips padded to a multiple of the warps per CTA (cta_jobs only)
     int no_skip;                   // test knob: never take the far-field (phi == +0) chunk shortcut
-    int dense_mode;                // 0 never use the straight-line dense tier, 1 predicted (default), 2 always (test knob)
+    int free_mode;                 // 1 (default): a CTA that met data-dependent work switches to per-warp claims; 0 never
     RowConst rc;                   // stencil constants
     ColdK ck;                      // constants of the data-dependent block
     uint32_t pk[20];               // Philox round keys: pk[2r] = seed_lo + r*W0, pk[2r+1] = seed_hi + r*W1
@@ -64,7 +65,7 @@ struct FastArgs {
     unsigned int* live_ctr;        // single-step kernel, probe launches only: counts the jobs that see live theta flags
     // linked strips: seam readiness is published per side as soon as the jobs touching that seam are done
     unsigned int* seam_ctr;        // [2]: low-side / high-side jobs completed in this launch (reset by the publisher)
-    unsigned int seam_jobs[2];     // jobs of this launch that touch the low / high seam
+    unsigned int seam_jobs[2];     // units of this launch (pair) that touch the low / high seam: jobs, or row ranges (two-step)
 };
 
 // Philox4x32-10 with the per-round keys (key + r * Weyl) precomputed on the host into the constant bank and the
@@ -116,9 +117,6 @@ struct FastGeom {
 #ifndef KOB_FAST_RB
 #define KOB_FAST_RB 4
 #endif
-#ifndef KOB_FAST_NST
-#define KOB_FAST_NST 4
-#endif
 #ifndef KOB_FAST_WARPS
 #define KOB_FAST_WARPS 8
 #endif
@@ -127,13 +125,10 @@ struct FastGeom {
 #endif
 constexpr int FAST_RB = KOB_FAST_RB;     // rows per TMA chunk (= unroll of the row loop)
 static_assert(FAST_RB >= 4, "the far-field shortcut needs a chunk to cover the 4-row history of the register windows");
-constexpr int FAST_NST = KOB_FAST_NST;   // TMA stages per warp
 constexpr int FAST_WARPS = KOB_FAST_WARPS;
 
-// one stage = phi box + T box, each padded to a multiple of 128 bytes (TMA shared-memory destination alignment)
+// an input box (4 rows x 68 columns), padded to a multiple of 128 bytes (TMA shared-memory destination alignment)
 constexpr int FAST_BOX_FLOATS = (FAST_RB * FastGeom::BW + 31) / 32 * 32;
-constexpr int FAST_STAGE_FLOATS = 2 * FAST_BOX_FLOATS;
-constexpr int FAST_WARP_BYTES = FAST_NST * FAST_STAGE_FLOATS * 4;
 
 // ---- PTX helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -177,64 +172,143 @@ __device__ __noinline__ void fast_mark_flags(uint32_t* self_f, uint32_t* lower_f
     mark_tile_flags<float>(a, x0, y0, tx, ty);
 }
 
-// Linked strips: a warp that finished a job touching the low (side 0) / high (side 1) seam counts it; the warp that
-// completes the side's last job of this launch publishes "epoch + 1" to that neighbour — its ghost rows are written and the
-// ghost rows this strip read from it are no longer needed — without waiting for the rest of the grid to drain.
-__device__ __forceinline__ void fast_seam_done(const StepArgs<float>& a, const FastArgs& f, bool low, bool high, int lane) {
+// Linked strips: a warp that finished work touching the low (side 0) / high (side 1) seam counts it (`n` units: 1 per job in
+// the single-step kernel, 1 per row range in the two-step launch pair); the warp that completes the side's last unit of this
+// launch (pair) publishes "epoch + sub" to that neighbour — its ghost rows are written and the ghost rows this strip read from
+// it are no longer needed — without waiting for the rest of the grid to drain.
+__device__ __forceinline__ void fast_seam_done(const StepArgs<float>& a, const FastArgs& f, bool low, bool high, unsigned int n,
+                                               unsigned int sub, int lane) {
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && n != 0u) {
         __threadfence_system();
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
             if (!(side ? high : low)) continue;
-            if (atomicAdd(&f.seam_ctr[side], 1u) + 1u == f.seam_jobs[side]) {
+            if (atomicAdd(&f.seam_ctr[side], n) + n == f.seam_jobs[side]) {
                 f.seam_ctr[side] = 0u;
                 __threadfence_system();
-                st_release_sys(side ? &a.upper.arrive[0] : &a.lower.arrive[1], a.epoch + 1u);
+                st_release_sys(side ? &a.upper.arrive[0] : &a.lower.arrive[1], a.epoch + sub);
             }
         }
     }
 }
 
+// ---- shared-memory plan of one warp of kob_step_fast (FAST_WARP_REGION bytes) ------------------------------------------------
+// Two layouts over the same bytes; a job uses one of them from its first TMA load to its last TMA store:
+//   ring 0 (lean and seam jobs):  4 input stages [phi box | T box]              + 2 output buffers [phi+ | T+]
+//   ring 1 (live jobs)         :  3 input stages [phi box | T box | theta box]  + 1 output buffer  [phi+ | T+ | theta]
+// Input boxes are 4 rows x 68 columns (they must start on a 16-byte boundary in global memory: box column 0 is cell
+// 60*strip - 4), output boxes 4 rows x 60 columns, each padded to a multiple of 128 bytes (TMA shared-memory alignment).  The lean path is HBM bound and wants the deep ring; live jobs are issue bound and want the
+// theta rows delivered by TMA instead of by LSU instructions and registers.
+constexpr int FAST_OUTC = FastGeom::OUTC;
+constexpr int FAST_OBOX_BYTES = (FAST_RB * FAST_OUTC * 4 + 127) / 128 * 128;           // 1024
+constexpr int FAST_BOX_BYTES = FAST_BOX_FLOATS * 4;                                    // 1152
+constexpr int FAST_R0_NST = 4, FAST_R1_NST = 3;
+constexpr int FAST_R0_NOBUF = 2, FAST_R1_NOBUF = 1;   // output buffers (ring 1: the store of chunk c has been read by the time chunk c+1 writes)
+constexpr int FAST_R0_STAGE = 2 * FAST_BOX_BYTES, FAST_R1_STAGE = 3 * FAST_BOX_BYTES;
+constexpr int FAST_R0_OUT = FAST_R0_NST * FAST_R0_STAGE, FAST_R1_OUT = FAST_R1_NST * FAST_R1_STAGE;
+constexpr int FAST_R0_OBUF = 2 * FAST_OBOX_BYTES, FAST_R1_OBUF = 3 * FAST_OBOX_BYTES;
+constexpr int FAST_R0_BYTES = FAST_R0_OUT + FAST_R0_NOBUF * FAST_R0_OBUF, FAST_R1_BYTES = FAST_R1_OUT + FAST_R1_NOBUF * FAST_R1_OBUF;
+constexpr int FAST_WARP_REGION = FAST_R0_BYTES > FAST_R1_BYTES ? FAST_R0_BYTES : FAST_R1_BYTES;
+constexpr int FAST_NBARS = FAST_R0_NST + FAST_R1_NST;
+static_assert(FAST_R0_OUT % 128 == 0 && FAST_R1_OUT % 128 == 0 && FAST_WARP_REGION % 128 == 0, "TMA boxes must sit on 128-byte boundaries");
+__host__ __device__ constexpr int fast_smem_bytes(int warps) { return warps * FAST_WARP_REGION + warps * FAST_NBARS * 8; }
+
+// TMA descriptors of the single-step kernel: inputs (68-wide phi / T / theta boxes) and outputs (60-wide boxes);
+// one per ping-pong buffer (phi, T) / per theta buffer.
+struct FastMapsIO {
+    CUtensorMap phi_in[2], t_in[2], th_in[2];
+    CUtensorMap phi_out[2], t_out[2], th_out[2];
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+                 "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // JM: 4 / 6 = compile-time integer mode, 0 = run-time integer mode (ck.jmode in 0..16), -1 = any real j (trig).
 // NOISE: 0 = off, 1 = Philox stream, 2 = host-injected field (a.noise_field; parity option, JM <= 0 instantiations only).
 template <int JM, int NOISE, bool ROT>
-__global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(const __grid_constant__ FastMaps maps, const StepArgs<float> a,
+__global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(const __grid_constant__ FastMapsIO maps, const StepArgs<float> a,
                                                                             const FastArgs f) {
     using G = FastGeom;
-    constexpr int CPL = G::CPL, BW = G::BW, RB = FAST_RB, NST = FAST_NST;
-    constexpr int STAGE_FLOATS = FAST_STAGE_FLOATS, BOX_FLOATS = FAST_BOX_FLOATS;
+    constexpr int CPL = G::CPL, BW = G::BW, RB = FAST_RB, OUTC = G::OUTC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    float* stages = reinterpret_cast<float*>(smem_raw) + (size_t)warp * NST * STAGE_FLOATS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * FAST_WARP_BYTES) + warp * NST;
+    // the warp index through a shuffle: tells the compiler it is warp-uniform, so that everything derived from it (shared-memory
+    // stage addresses, barriers, job geometry, TMA operands) can live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned char* region = smem_raw + (size_t)warp * FAST_WARP_REGION;
+    uint64_t* bars0 = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nwarps * FAST_WARP_REGION) + warp * FAST_NBARS;
+    uint64_t* bars1 = bars0 + FAST_R0_NST;
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < FAST_NBARS; ++s) mbar_init(&bars0[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    const CUtensorMap* map_phi = a.cur ? &maps.phi[1] : &maps.phi[0];
-    const CUtensorMap* map_t = a.cur ? &maps.t[1] : &maps.t[0];
+    const int tcur = a.tcur;                                 // which theta buffer is current (the two-step kernel flips them)
+    const CUtensorMap* map_phi = &maps.phi_in[a.cur];
+    const CUtensorMap* map_t = &maps.t_in[a.cur];
+    const CUtensorMap* map_th = &maps.th_in[tcur];
+    const CUtensorMap* omap_phi = &maps.phi_out[a.cur ^ 1];
+    const CUtensorMap* omap_t = &maps.t_out[a.cur ^ 1];
+    const CUtensorMap* omap_th = &maps.th_out[tcur];
     float* __restrict__ phi_out = a.self.phi[a.cur ^ 1];
     float* __restrict__ t_out = a.self.t[a.cur ^ 1];
     const long long pitch = a.pitch;
-    unsigned int gchunk = 0;   // chunks consumed so far by this warp: stage = gchunk % NST, parity = (gchunk / NST) & 1
+    unsigned int gch0 = 0, gch1 = 0;   // chunks consumed so far per ring: stage = g % NST, parity = (g / NST) & 1
 
+    // Job claims.  Jobs are numbered (segment, strip) with the strips padded to a multiple of the CTA's warps; the global
+    // counter is ALWAYS advanced by a whole group of `nwarps` adjacent strips of one segment, so that (a) the warps of a
+    // lock-step group share the segment, hence the chunk count, and (b) every CTA overshoots the queue by exactly one group —
+    // the host predicts the counter (job_base of the next launch) from that.  CTA mode hands a group out behind a block
+    // barrier; FREE mode (after the CTA met data-dependent work) hands the slots of a group out to whichever warp comes
+    // first, without any barrier: the warp that takes slot 0 fetches the group and publishes it in a small ring.
     __shared__ unsigned long long s_job;
+    __shared__ unsigned long long s_gbase[8];
+    __shared__ unsigned int s_gid[8];
+    __shared__ unsigned int s_taken;
+    if (threadIdx.x < 8) s_gid[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_taken = 0u;
+    __syncthreads();
     const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
     const int njobs_q = nsp * f.nseg;
+    bool cta_claims = f.cta_jobs != 0;                       // CTA mode (block-uniform; may switch to FREE mode once)
+    int busy_run = 0;                                        // consecutive CTA-mode groups with data-dependent work
     for (;;) {
         unsigned long long jraw = 0;
-        if (f.cta_jobs) {
+        if (cta_claims) {
             __syncthreads();
             if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
             __syncthreads();
             jraw = s_job + (unsigned long long)warp;
             if (s_job >= (unsigned long long)njobs_q) break;
-        } else {
+        } else if (f.cta_jobs) {                             // FREE mode
+            if (lane == 0) {
+                const unsigned int slot = atomicAdd(&s_taken, 1u), g = slot / (unsigned int)nwarps, k = slot - g * (unsigned int)nwarps;
+                volatile unsigned int* gid = &s_gid[g & 7u];
+                volatile unsigned long long* gb = &s_gbase[g & 7u];
+                if (k == 0u) {
+                    *gb = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+                    __threadfence_block();
+                    *gid = g + 1u;
+                } else {
+                    while (*gid != g + 1u) __nanosleep(20);
+                    __threadfence_block();
+                }
+                jraw = *gb + (unsigned long long)k;
+            }
+            jraw = __shfl_sync(0xffffffffu, jraw, 0);
+            if (jraw >= (unsigned long long)njobs_q) break;
+        } else {                                             // narrow grids / KOB_FAST_CTA=0: every warp claims single jobs
             if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
             jraw = __shfl_sync(0xffffffffu, jraw, 0);
             if (jraw >= (unsigned long long)njobs_q) break;
@@ -246,15 +320,15 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
         const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);
         const int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
         const int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
-        const int xs = strip * G::OUTC - CPL;            // first pass-1 column of the warp (lane 0, halo)
+        const int xs = strip * OUTC - CPL;               // first pass-1 column of the warp (lane 0, halo)
         const int x = xs + CPL * lane;                   // first cell of this lane
         const bool mid_lane = lane >= 1 && lane <= 30;
         const bool touch_low = y0 < GY + 1, touch_high = y1 > a.ny - GY - 1;
 
         if (a.linked) {
             if (lane == 0) {
-                if (touch_low) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
-                if (touch_high) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
+                if (touch_low) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2], 1u);
+                if (touch_high) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2], 1u);
             }
             __syncwarp();
         }
@@ -275,89 +349,241 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
         }
         const bool live = livemask != 0u;
         if (f.live_ctr && live && lane == 0 && strip < f.nstrips) atomicAdd(f.live_ctr, 1u);     // density probe (adaptive policy)
-        // seam job: touches the first/last GXR columns or GY rows -> alias stores, ragged right edge
-        const bool seam = strip == 0 || (strip + 1) * G::OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
+        // seam job: touches the first/last GXR columns or GY rows (alias stores, ragged right edge), or its height is not a
+        // multiple of the chunk (the TMA output boxes of the interior paths are whole chunks) -> generic LSU path
+        const bool seam = strip == 0 || (strip + 1) * OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY || ((y1 - y0) & (RB - 1)) != 0;
 
         const int nrows = (y1 - y0) + 4;                 // streamed phi rows y0-2 .. y1+1
         const int nch = (nrows + RB - 1) / RB;
         // CTA-wide jobs: the 8 adjacent strips advance in lock-step (one barrier per chunk) so that a row is fetched as
         // 1920 contiguous bytes.  cta_jobs == 2: only while none of the 8 does data-dependent work (live theta / seam) —
         // there the rows take unequal time and the barrier would only add waiting.
-        bool lock = f.cta_jobs == 1;
-        if (f.cta_jobs == 2) lock = !__syncthreads_or((live || seam) && strip < f.nstrips);
-        if (strip >= f.nstrips) {                        // padding job (cta_jobs): only keep the CTA's barriers company
+        bool lock = cta_claims && f.cta_jobs == 1;
+        if (cta_claims && f.cta_jobs == 2) {
+            const bool busy = __syncthreads_or((live || seam) && strip < f.nstrips);
+            lock = !busy;
+            // developed field (two busy groups in a row — isolated crystals in a sparse field do not do that): from the next
+            // claim on the warps of this CTA take their slots without a barrier (FREE mode; same counter, same groups)
+            busy_run = busy ? busy_run + 1 : 0;
+            if (busy_run >= 2 && f.free_mode) cta_claims = false;
+        }
+        if (strip >= f.nstrips) {                        // padding job: only keep the CTA's barriers company
             if (lock)
                 for (int c = 0; c < nch; ++c) __syncthreads();
             continue;
         }
-        const int box_x = xs - CPL + GX;                 // padded x of box column 0
-        auto issue = [&](int c) {                        // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
-            const unsigned int gi = gchunk + (unsigned int)c;
-            const int st = gi % NST;
-            float* dst = stages + st * STAGE_FLOATS;
-            mbar_expect_tx(&bars[st], 2 * RB * BW * 4);
-            const int yr = y0 - 2 + c * RB + GY;         // padded row of the chunk's first phi row
-            tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
-            tma_load_2d(dst + BOX_FLOATS, map_t, box_x, yr - 1, &bars[st]);
-        };
-        if (lane == 0) {
-            for (int c = 0; c < NST && c < nch; ++c) issue(c);
-        }
-
+        const int box_x = xs - CPL + GX;                 // padded x of the phi / T box column 0
         bool assigned_any = false;
+        const unsigned int nvalid = (unsigned int)(y1 - y0);
+        const unsigned int nstore = mid_lane ? nvalid : 0u;    // rows this lane stores
 
-        // The row loop, instantiated three times.  MODE 0 (lean): interior strip, theta all zero in the footprint.
-        // MODE 1 (live): interior strip, held theta is read.  MODE 2 (seam): additionally the ragged right edge and the
-        // alias stores.
-        auto body = [&](auto mode_tag) {
+        // ---- interior jobs (MODE 0 lean: theta all zero in the footprint; MODE 1 live: held theta is read): every byte in and
+        // out of the warp moves by TMA.  Chunk c consumes phi rows y0-2+4c .. +3 and produces rows y0+4(c-1) .. +3. ----
+        auto body_io = [&](auto mode_tag) {
             constexpr int MODE = decltype(mode_tag)::value;
-            constexpr bool GEN = MODE != 0, SEAM = MODE == 2;
+            constexpr bool GEN = MODE == 1;
+            constexpr int NST = GEN ? FAST_R1_NST : FAST_R0_NST, STAGE = GEN ? FAST_R1_STAGE : FAST_R0_STAGE;
+            constexpr int OUT0 = GEN ? FAST_R1_OUT : FAST_R0_OUT, OBUF = GEN ? FAST_R1_OBUF : FAST_R0_OBUF;
+            constexpr int NOBUF = GEN ? FAST_R1_NOBUF : FAST_R0_NOBUF;
+            uint64_t* bars = GEN ? bars1 : bars0;
+            unsigned int& gchunk = GEN ? gch1 : gch0;
+            auto issue = [&](int c) {                    // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                unsigned char* dst = region + st * STAGE;
+                mbar_expect_tx(&bars[st], (GEN ? 3 : 2) * RB * BW * 4);
+                const int yr = y0 - 2 + c * RB + GY;     // padded row of the chunk's first phi row
+                tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
+                tma_load_2d(dst + FAST_BOX_BYTES, map_t, box_x, yr - 1, &bars[st]);
+                if (GEN) tma_load_2d(dst + 2 * FAST_BOX_BYTES, map_th, box_x, yr - 1, &bars[st]);     // theta rows = the T rows
+            };
+            if (lane == 0) {
+                for (int c = 0; c < NST && c < nch; ++c) issue(c);
+            }
             RowState S;
             S.clear();
-            // GEN: theta of the held cells, prefetched two rows ahead: thp0 = theta(r-1), thp1 = theta(r)
+            bool prevz = false;                          // !GEN: the previous chunk's phi rows were all +0
+            float2 th_hold = f2(0.f);                    // GEN: angle of the row produced by the last iteration of the previous chunk
+            const int lane_out = (lane - 1) * CPL * 4;   // byte offset of this lane's pair in an output row (mid lanes)
+
+            for (int c = 0; c < nch; ++c) {
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                if (lock) __syncthreads();                                          // adjacent strips advance together
+                mbar_wait(&bars[st], (gi / NST) & 1u);
+                const unsigned char* stage = region + st * STAGE;
+                const float* sp = reinterpret_cast<const float*>(stage) + CPL * lane + CPL;   // this lane's own phi cells
+                const float* stt = sp + FAST_BOX_FLOATS;                            // T rows (one row behind)
+                const float* sth = stt + FAST_BOX_FLOATS;                           // GEN: theta rows (same rows as T)
+                unsigned char* obuf = region + OUT0 + (NOBUF == 2 ? (c & 1) : 0) * OBUF;   // output boxes of this chunk
+                const bool store = c > 0;                                           // chunk 0 only warms the windows up
+                const int yrel0 = c * RB - 4;                                       // (r - 2) - y0 for rr = 0
+                if (NOBUF == 1 && c > 1) {               // single output buffer: the previous chunk's boxes must have been read
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                if (GEN && store && mid_lane) *reinterpret_cast<float2*>(obuf + 2 * FAST_OBOX_BYTES + lane_out) = th_hold;
+                bool skipped = false;
+                if (!GEN) {
+                    // ---- far field: phi == +0 on all 64 own columns of this chunk's RB rows AND of the previous RB
+                    // rows.  Every phi term of the step is then exactly +0 and the register windows already sit at
+                    // their all-zero-input fixed point (each is a function of the last <= 5 streamed rows only), so
+                    // the chunk reduces to the T diffusion; outputs are bit-identical to the full path. ----
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * BW]) | __float_as_uint(sp[rr * BW + 1]);
+                    const bool curz = !__any_sync(0xffffffffu, bits != 0u);
+                    skipped = curz && prevz && !f.no_skip;
+                    prevz = curz;
+                    if (skipped) {
+#pragma unroll
+                        for (int rr = 0; rr < RB; ++rr) {
+                            const float* trow = stt + rr * BW;
+                            const float2 nt_ = row_tonly(S, f.rc, *reinterpret_cast<const float2*>(trow), trow[-1], trow[CPL]);
+                            if (store && mid_lane) {
+                                *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = f2(0.f);
+                                *reinterpret_cast<float2*>(obuf + FAST_OBOX_BYTES + rr * (OUTC * 4) + lane_out) = nt_;
+                            }
+                        }
+                    }
+                }
+                if (!skipped) {
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) {
+                        const unsigned int yrel = (unsigned int)(yrel0 + rr);       // row of pass 2, relative to y0
+                        const float* prow = sp + rr * BW;
+                        const float* trow = stt + rr * BW;
+                        const float2 pn = *reinterpret_cast<const float2*>(prow);
+                        const float2 tn = *reinterpret_cast<const float2*>(trow);
+                        float th_in[CPL] = {0.f, 0.f};
+                        if (GEN) {
+                            const float2 v = *reinterpret_cast<const float2*>(sth + rr * BW);
+                            th_in[0] = v.x; th_in[1] = v.y;
+                        }
+                        float2 np_, nt_, th2 = f2(0.f);
+                        bool asg[CPL];
+                        const int y = y0 + (int)yrel;
+                        auto draw = [&]() -> float2 {
+                            if (NOISE == 2) {
+                                float2 rq;
+                                rq.x = (yrel < nvalid ? __ldg(&a.noise_field[(long long)x + (long long)a.nx * y]) : 0.5f) - 0.5f;
+                                rq.y = (yrel < nvalid ? __ldg(&a.noise_field[(long long)(x + 1) + (long long)a.nx * y]) : 0.5f) - 0.5f;
+                                return rq;
+                            }
+                            return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, (rr & 1) == 0, lane);
+                        };
+                        if ((rr & 1) == 0) S.have_next = false;
+                        const bool vote = row_full<JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                               th_in, draw, np_, nt_, th2, asg);
+                        if (store && mid_lane) {
+                            *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = np_;
+                            *reinterpret_cast<float2*>(obuf + FAST_OBOX_BYTES + rr * (OUTC * 4) + lane_out) = nt_;
+                        }
+                        if (GEN) {
+                            // angle of row r-1 after this step: re-assigned or kept.  Rows are written back whole (a held cell gets
+                            // the bits it had), one row ahead of phi/T: the last row of a chunk waits in th_hold for the next box.
+                            const float2 thv = make_float2((vote && asg[0]) ? th2.x : th_in[0], (vote && asg[1]) ? th2.y : th_in[1]);
+                            if (rr < RB - 1) {
+                                if (store && mid_lane) *reinterpret_cast<float2*>(obuf + 2 * FAST_OBOX_BYTES + (rr + 1) * (OUTC * 4) + lane_out) = thv;
+                            } else {
+                                th_hold = thv;
+                            }
+                            if (vote && yrel + 1u < nstore) assigned_any |= asg[0] || asg[1];
+                        } else if (vote && yrel + 1u < nstore) {
+                            // lean job: theta is zero in the whole footprint and is only written where re-assigned (rare: the front
+                            // of a crystal entering a far-field job)
+                            float* pth = a.self.theta + pidx<float>(pitch, x, y + 1);
+                            if (asg[0]) pth[0] = th2.x;
+                            if (asg[1]) pth[1] = th2.y;
+                            assigned_any |= asg[0] || asg[1];
+                        }
+                    }
+                }
+                // ---- this chunk's output boxes leave by TMA; the next chunk's input is requested ----
+                if (store) fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (store) {
+                        const int ox = strip * OUTC + GX, oy = y0 + (c - 1) * RB + GY;
+                        tma_store_2d(omap_phi, ox, oy, obuf);
+                        tma_store_2d(omap_t, ox, oy, obuf + FAST_OBOX_BYTES);
+                        if (GEN) tma_store_2d(omap_th, ox, oy, obuf + 2 * FAST_OBOX_BYTES);
+                        tma_store_commit();
+                        if (NOBUF == 2) tma_store_wait_read<1>();   // the other buffer (chunk c-1's boxes) has been read: free for chunk c+1
+                    }
+                    if (c + NST < nch) issue(c + NST);
+                }
+                __syncwarp();
+            }
+            gchunk += (unsigned int)nch;
+            if (lane == 0) tma_store_wait_read<0>();     // the next job may lay the region out differently
+            __syncwarp();
+        };
+
+        // ---- seam jobs (MODE 2): the ragged right edge, the alias stores to ghost columns / neighbour strips, arbitrary job
+        // heights; theta by LSU loads two rows ahead and predicated stores.  Ring 0 input stages. ----
+        auto body_seam = [&]() {
+            constexpr int NST = FAST_R0_NST, STAGE = FAST_R0_STAGE;
+            uint64_t* bars = bars0;
+            unsigned int& gchunk = gch0;
+            auto issue = [&](int c) {
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                unsigned char* dst = region + st * STAGE;
+                mbar_expect_tx(&bars[st], 2 * RB * BW * 4);
+                const int yr = y0 - 2 + c * RB + GY;
+                tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
+                tma_load_2d(dst + FAST_BOX_BYTES, map_t, box_x, yr - 1, &bars[st]);
+            };
+            if (lane == 0) {
+                for (int c = 0; c < NST && c < nch; ++c) issue(c);
+            }
+            RowState S;
+            S.clear();
+            // theta of the held cells, prefetched two rows ahead: thp0 = theta(r-1), thp1 = theta(r)
             float thp0[CPL] = {0.f, 0.f}, thp1[CPL] = {0.f, 0.f};
             // running pointers to cell (x, r-2) of the output arrays / theta
             const long long o2 = pidx<float>(pitch, x, y0 - 4);
             float* pphi = phi_out + o2;
             float* ptt = t_out + o2;
-            const unsigned int nvalid = (unsigned int)(y1 - y0);
-            const unsigned int nstore = mid_lane ? nvalid : 0u;    // rows this lane stores
-            bool prevz = false;                    // !GEN: the previous chunk's phi rows were all +0
-            bool dense = f.dense_mode == 2;        // MODE 1: every row of the previous chunk did data-dependent work
             float* pthe = a.self.theta + (o2 + pitch);   // theta of cell (x, r-1): the row pass 1 re-assigns
             const long long pitch2 = 2 * pitch;
-
-            // one row: load, update (kob_row.cuh), store phi+/T+ of row r-2 and the re-assigned angles of row r-1
-            auto row = [&](auto dense_tag, int rr, const float* sp, const float* stt, int yrel0, bool lrow_c) -> bool {
-                constexpr bool DENSE = decltype(dense_tag)::value;
-                const unsigned int yrel = (unsigned int)(yrel0 + rr);               // row of pass 2, relative to y0
-                const float* prow = sp + rr * BW;
-                const float* trow = stt + rr * BW;
-                const float2 pn = *reinterpret_cast<const float2*>(prow);
-                const float2 tn = *reinterpret_cast<const float2*>(trow);
-                float2 np_, nt_, th2;
-                bool asg[CPL];
-                const int y = y0 + (int)yrel;
-                auto draw = [&]() -> float2 {
-                    if (NOISE == 2) {
-                        float2 rq;
-                        rq.x = ((x >= 0 && x < a.nx && yrel < nvalid) ? __ldg(&a.noise_field[(long long)x + (long long)a.nx * y]) : 0.5f) - 0.5f;
-                        rq.y = ((x + 1 >= 0 && x + 1 < a.nx && yrel < nvalid) ? __ldg(&a.noise_field[(long long)(x + 1) + (long long)a.nx * y]) : 0.5f) - 0.5f;
-                        return rq;
-                    }
-                    return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, (rr & 1) == 0, lane);
-                };
-                if ((rr & 1) == 0) S.have_next = false;
-                const bool vote = row_full<JM, NOISE != 0, ROT, GEN, DENSE>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
-                                                                       thp0, draw, np_, nt_, th2, asg);
-                // ---- store the re-assigned angles of owned cells of row r-1 ----
-                if (vote && yrel + 1u < nstore) {
-                    if (!SEAM) {
-                        if (asg[0]) pthe[0] = th2.x;
-                        if (asg[1]) pthe[1] = th2.y;
-                        // (flags are conservative hints: a dense row marks its blocks without looking)
-                        if (DENSE) assigned_any = true; else assigned_any |= asg[0] || asg[1];
-                    } else {
+            for (int c = 0; c < nch; ++c) {
+                const unsigned int gi = gchunk + (unsigned int)c;
+                const int st = gi % NST;
+                mbar_wait(&bars[st], (gi / NST) & 1u);
+                const float* sp = reinterpret_cast<const float*>(region + st * STAGE) + CPL * lane + CPL;
+                const float* stt = sp + FAST_BOX_FLOATS;
+                const int yrel0 = c * RB - 4;
+                bool lrow_c = false;          // some theta-flag row under this chunk's prefetch rows (r+1) is live
+                if (live) {
+                    const int f0 = ((y0 + yrel0 + 3 + GY) >> 5) - fby0, f1 = ((y0 + yrel0 + RB + 2 + GY) >> 5) - fby0;   // FBY == 32
+                    lrow_c = ((livemask >> min(max(f0, 0), 31)) | (livemask >> min(max(f1, 0), 31))) & 1u;
+                }
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const unsigned int yrel = (unsigned int)(yrel0 + rr);
+                    const float* prow = sp + rr * BW;
+                    const float* trow = stt + rr * BW;
+                    const float2 pn = *reinterpret_cast<const float2*>(prow);
+                    const float2 tn = *reinterpret_cast<const float2*>(trow);
+                    float2 np_, nt_, th2 = f2(0.f);
+                    bool asg[CPL];
+                    const int y = y0 + (int)yrel;
+                    auto draw = [&]() -> float2 {
+                        if (NOISE == 2) {
+                            float2 rq;
+                            rq.x = ((x >= 0 && x < a.nx && yrel < nvalid) ? __ldg(&a.noise_field[(long long)x + (long long)a.nx * y]) : 0.5f) - 0.5f;
+                            rq.y = ((x + 1 >= 0 && x + 1 < a.nx && yrel < nvalid) ? __ldg(&a.noise_field[(long long)(x + 1) + (long long)a.nx * y]) : 0.5f) - 0.5f;
+                            return rq;
+                        }
+                        return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, (rr & 1) == 0, lane);
+                    };
+                    if ((rr & 1) == 0) S.have_next = false;
+                    const bool vote = row_full<JM, NOISE != 0, ROT, true>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                            thp0, draw, np_, nt_, th2, asg);
+                    // ---- store the re-assigned angles of owned cells of row r-1 ----
+                    if (vote && yrel + 1u < nstore) {
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
                             if (asg[k] && x + k < a.nx) {
@@ -375,129 +601,57 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                             }
                         }
                     }
-                }
-                // ---- store phi+, T+ of row r-2 ----
-                if (yrel < nstore) {
-                    if (!SEAM) {
-                        *reinterpret_cast<float2*>(pphi) = np_;
-                        *reinterpret_cast<float2*>(ptt) = nt_;
-                    } else if (y < GY || y >= a.ny - GY) {          // rows on the strip seam: every alias (rare)
+                    // ---- store phi+, T+ of row r-2 ----
+                    if (yrel < nstore) {
+                        if (y < GY || y >= a.ny - GY) {          // rows on the strip seam: every alias (rare)
 #pragma unroll
-                        for (int k = 0; k < CPL; ++k)
-                            if (x + k < a.nx) {
-                                fast_store_edge(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, k ? np_.y : np_.x);
-                                fast_store_edge(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, k ? nt_.y : nt_.x);
-                            }
-                    } else {                                         // interior rows: own cell + ghost-column copy
+                            for (int k = 0; k < CPL; ++k)
+                                if (x + k < a.nx) {
+                                    fast_store_edge(phi_out, a.lower.phi[a.cur ^ 1], a.upper.phi[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, k ? np_.y : np_.x);
+                                    fast_store_edge(t_out, a.lower.t[a.cur ^ 1], a.upper.t[a.cur ^ 1], pitch, a.nx, a.ny, a.lower.ny, x + k, y, k ? nt_.y : nt_.x);
+                                }
+                        } else {                                 // interior rows: own cell + ghost-column copy
 #pragma unroll
-                        for (int k = 0; k < CPL; ++k)
-                            if (x + k < a.nx) {
-                                const float vp = k ? np_.y : np_.x, vt = k ? nt_.y : nt_.x;
-                                pphi[k] = vp;
-                                ptt[k] = vt;
-                                if (x + k < GXR) { pphi[k + a.nx] = vp; ptt[k + a.nx] = vt; }
-                                if (x + k >= a.nx - GXR) { pphi[k - a.nx] = vp; ptt[k - a.nx] = vt; }
-                            }
+                            for (int k = 0; k < CPL; ++k)
+                                if (x + k < a.nx) {
+                                    const float vp = k ? np_.y : np_.x, vt = k ? nt_.y : nt_.x;
+                                    pphi[k] = vp;
+                                    ptt[k] = vt;
+                                    if (x + k < GXR) { pphi[k + a.nx] = vp; ptt[k + a.nx] = vt; }
+                                    if (x + k >= a.nx - GXR) { pphi[k - a.nx] = vp; ptt[k - a.nx] = vt; }
+                                }
+                        }
                     }
-                }
-                // ---- GEN: prefetch theta of row r+1 (pass-1 row of the iteration after next) ----
-                if (GEN) {
+                    // ---- prefetch theta of row r+1 (pass-1 row of the iteration after next) ----
                     thp0[0] = thp1[0]; thp0[1] = thp1[1];
                     thp1[0] = thp1[1] = 0.f;
                     if (lrow_c && yrel + 4u <= nvalid + 1u) {                            // theta rows y0-1 .. y1
                         const float* pf = pthe + pitch2;                                 // theta(x, r+1)
-                        if (SEAM) {
 #pragma unroll
-                            for (int k = 0; k < CPL; ++k)
-                                if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(pf + k);
-                        } else {
-                            const float2 v = __ldg(reinterpret_cast<const float2*>(pf));
-                            thp1[0] = v.x; thp1[1] = v.y;
-                        }
+                        for (int k = 0; k < CPL; ++k)
+                            if (x + k < a.nx + GXR && x + k >= -GXR) thp1[k] = __ldg(pf + k);
                     }
-                }
-                pphi += pitch;
-                ptt += pitch;
-                pthe += pitch;
-                return vote;
-            };
-
-            for (int c = 0; c < nch; ++c) {
-                const unsigned int gi = gchunk + (unsigned int)c;
-                const int st = gi % NST;
-                if (lock) __syncthreads();                                          // adjacent strips advance together
-                mbar_wait(&bars[st], (gi / NST) & 1u);
-                const float* sp = stages + st * STAGE_FLOATS + CPL * lane + CPL;   // this lane's own phi cells
-                const float* stt = sp + BOX_FLOATS;                                // T rows (one row behind)
-                const int yrel0 = c * RB - 4;                                       // (r - 2) - y0 for rr = 0
-                if (!GEN) {
-                    // ---- far field: phi == +0 on all 64 own columns of this chunk's RB rows AND of the previous RB
-                    // rows.  Every phi term of the step is then exactly +0 and the register windows already sit at
-                    // their all-zero-input fixed point (each is a function of the last <= 5 streamed rows only), so
-                    // the chunk reduces to the T diffusion; outputs are bit-identical to the full path. ----
-                    uint32_t bits = 0u;
-#pragma unroll
-                    for (int rr = 0; rr < RB; ++rr) bits |= __float_as_uint(sp[rr * BW]) | __float_as_uint(sp[rr * BW + 1]);
-                    const bool curz = !__any_sync(0xffffffffu, bits != 0u);
-                    const bool skip = curz && prevz && !f.no_skip;
-                    prevz = curz;
-                    if (skip) {
-#pragma unroll
-                        for (int rr = 0; rr < RB; ++rr) {
-                            const unsigned int yrel = (unsigned int)(yrel0 + rr);
-                            const float* trow = stt + rr * BW;
-                            const float2 nt_ = row_tonly(S, f.rc, *reinterpret_cast<const float2*>(trow), trow[-1], trow[CPL]);
-                            if (yrel < nstore) {
-                                *reinterpret_cast<float2*>(pphi) = f2(0.f);
-                                *reinterpret_cast<float2*>(ptt) = nt_;
-                            }
-                            pphi += pitch;
-                            ptt += pitch;
-                            pthe += pitch;
-                        }
-                        __syncwarp();
-                        if (lane == 0 && c + NST < nch) issue(c + NST);
-                        continue;
-                    }
-                }
-                bool lrow_c = false;          // GEN: some theta-flag row under this chunk's prefetch rows (r+1) is live
-                if (GEN && live) {
-                    const int f0 = ((y0 + yrel0 + 3 + GY) >> 5) - fby0, f1 = ((y0 + yrel0 + RB + 2 + GY) >> 5) - fby0;   // FBY == 32
-                    lrow_c = ((livemask >> min(max(f0, 0), 31)) | (livemask >> min(max(f1, 0), 31))) & 1u;
-                }
-#ifdef KOB_DEV_ONLY_DENSE
-                if (true) {
-#else
-                if (MODE == 1 && dense) {
-#endif
-                    // DENSE tier: rows 0..2 run the data-dependent block without asking; the last row votes again and so
-                    // decides about the next chunk
-#pragma unroll
-                    for (int rr = 0; rr < RB - 1; ++rr) row(std::true_type{}, rr, sp, stt, yrel0, lrow_c);
-                    dense = row(std::false_type{}, RB - 1, sp, stt, yrel0, lrow_c) || f.dense_mode == 2;
-                } else {
-                    bool all = true;
-#pragma unroll
-                    for (int rr = 0; rr < RB; ++rr) all &= row(std::false_type{}, rr, sp, stt, yrel0, lrow_c);
-                    dense = (all && f.dense_mode != 0) || f.dense_mode == 2;
+                    pphi += pitch;
+                    ptt += pitch;
+                    pthe += pitch;
                 }
                 __syncwarp();
                 if (lane == 0 && c + NST < nch) issue(c + NST);
             }
+            gchunk += (unsigned int)nch;
         };
-#ifdef KOB_DEV_ONLY_DENSE   // developer harness (scripts/dev/sass_lines.sh): only the live row loop, for SASS inspection
-        body(std::integral_constant<int, 1>{});
+#ifdef KOB_DEV_ONLY_LIVE   // developer harness (scripts/dev/sass_lines.sh): only the live row loop, for SASS inspection
+        body_io(std::integral_constant<int, 1>{});
 #else
-        if (seam) body(std::integral_constant<int, 2>{});
-        else if (live) body(std::integral_constant<int, 1>{});
-        else body(std::integral_constant<int, 0>{});
+        if (seam) body_seam();
+        else if (live) body_io(std::integral_constant<int, 1>{});
+        else body_io(std::integral_constant<int, 0>{});
 #endif
-
-        gchunk += (unsigned int)nch;
         if (__any_sync(0xffffffffu, assigned_any) && lane == 0) fast_mark_flags(a.self.tflags, a.lower.tflags, a.upper.tflags, a.lower.ny, a.upper.ny, a.nx, a.ny, a.nfbx, a.nfby,
-                            strip * G::OUTC, y0, G::OUTC, y1 - y0);
-        if (a.linked && (touch_low || touch_high)) fast_seam_done(a, f, touch_low, touch_high, lane);
+                            strip * OUTC, y0, OUTC, y1 - y0);
+        if (a.linked && (touch_low || touch_high)) fast_seam_done(a, f, touch_low, touch_high, 1u, 1u, lane);
     }
+    if (lane == 0) tma_store_wait_all();                 // every output box has landed before the warp retires
 }
 
 }  // namespace kob

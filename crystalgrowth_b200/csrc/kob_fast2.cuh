@@ -75,7 +75,7 @@ __device__ __forceinline__ void f2_row(RowState& S, const FastArgs& f, float2 pn
     if (even) S.have_next = false;
     bool asg[2];
     float2 th2;
-    row_full<JM, NOISE, ROT, GEN, false>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
+    row_full<JM, NOISE, ROT, GEN>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
     th_eff[0] = asg[0] ? th2.x : (GEN ? th_old_in[0] : 0.f);
     th_eff[1] = asg[1] ? th2.y : (GEN ? th_old_in[1] : 0.f);
     any_asg |= asg[0] || asg[1];
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
         const bool seam = strip == 0 || (strip + 1) * F2_OUTC > a.nx - GXR || y0 < GY || y1 > a.ny - GY;
         if (a.linked) {
             if (lane == 0) {
-                if (y0 < GY + 2) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
-                if (y1 > a.ny - GY - 1) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
+                if (y0 < GY + 2) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2], 2u);
+                if (y1 > a.ny - GY - 1) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2], 2u);
             }
             __syncwarp();
         }
@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
             if (lane < F2_RANGES && ((need_out >> lane) & 1u))
                 w.list[pos + __popc(need_out & ((1u << lane) - 1u))] = (sq * f.nstrips + strip) * F2_RANGES + lane;   // unpadded job numbering
         }
+        // linked strips: the row ranges of a seam job this pass completed itself count towards the side's early publish;
+        // the listed ones are counted by the general pass
+        if (a.linked && (y0 < GY + 2 || y1 > a.ny - GY - 1))
+            fast_seam_done(a, f, y0 < GY + 2, y1 > a.ny - GY - 1, (unsigned int)(F2_RANGES - __popc(need_out)), 2u, lane);
     }
 }
 
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         const int seg_ = sq == 0 ? 0 : (sq == 1 ? f.nseg - 1 : sq - 1);     // the two torus-seam segments first
         int y0 = seg_ < f.nseg_a ? seg_ * f.yj : f.nseg_a * f.yj + (seg_ - f.nseg_a) * f.yj_b;
         int y1 = min(y0 + (seg_ < f.nseg_a ? f.yj : f.yj_b), a.ny);
+        const bool job_low = y0 < GY + 2, job_high = y1 > a.ny - GY - 1;   // the JOB touches a strip seam (early publish, in row ranges)
         if (sub >= 0) {
             const int q = f2_range_rows(y1 - y0);            // rows per sub-job, a multiple of 4
             y0 += sub * q;
@@ -353,8 +358,8 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
 
         if (a.linked && real_job) {
             if (lane == 0) {
-                if (y0 < GY + 2) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2]);
-                if (y1 > a.ny - GY - 1) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2]);
+                if (y0 < GY + 2) wait_flag(&a.self.arrive[0], a.epoch, &a.self.arrive[2], 2u);
+                if (y1 > a.ny - GY - 1) wait_flag(&a.self.arrive[1], a.epoch, &a.self.arrive[2], 2u);
             }
             __syncwarp();
         }
@@ -571,8 +576,9 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
         if (__any_sync(0xffffffffu, assigned_any) && lane == 0)
             fast_mark_flags(a.self.tflags, a.lower.tflags, a.upper.tflags, a.lower.ny, a.upper.ny, a.nx, a.ny, a.nfbx, a.nfby,
                             strip * F2_OUTC, y0, F2_OUTC, y1 - y0);
+        if (a.linked && real_job && (job_low || job_high))
+            fast_seam_done(a, f, job_low, job_high, sub >= 0 ? 1u : (unsigned int)F2_RANGES, 2u, lane);
     }
-    signal_neighbours(a);
 }
 
 }  // namespace kob

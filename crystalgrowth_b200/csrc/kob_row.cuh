@@ -104,9 +104,11 @@ KOB_RD void cpow2_rt(int j, float2 c, float2 s, float2& C, float2& S) {
 // Loop constants of the data-dependent block (kernel parameters: they sit in the constant bank / uniform registers).
 struct ColdK {
     float e;                         // dead-band: FLT_EPSILON (src/Kobayashi.cpp:154)
-    float off1, off2, off3, off4;    // re-assigned angle = off[quadrant of (gx, gy)] + atan(w):
-                                     //   Q1 pi/4, Q2 PI_F - pi/4, Q3 PI_F + pi/4, Q4 2 PI_F - pi/4   (:160-167)
+    float off_c, off_y, off_s;       // re-assigned angle = off_c + off_y sy + off_s sx sy + atan(w): PI_F, -PI_F/2, pi/4 - PI_F/2
+                                     //   (Q1 pi/4, Q2 PI_F - pi/4, Q3 PI_F + pi/4, Q4 2 PI_F - pi/4; :160-167)
     float half_pi;                   // 0.5 PI_F (:156-158)
+    float cfl_p, sfl_p, cfl_m, sfl_m;// cos / sin (j (+-PI_F/2 - theta0)): anisotropy of a case-A cell (gy > 0 / gy < 0)
+    float j_rev, jth0_rev;           // j / 2pi and -j theta0 / 2pi: j (theta - theta0) in revolutions (held angles)
     float ebd, epsbar, neg_ebjd;     // eps = epsbar + (epsbar delta) cos, eps' = ((-epsbar j) delta) sin   (:170-171)
     float eps0, epsd0;               // eps, eps' of a cell holding theta = 0
     float cj0, sj0;                  // cos / sin (j theta0): rotation of the anisotropy axes (extension)
@@ -122,9 +124,6 @@ __device__ __noinline__ void fast_sincos(float arg, float* s, float* c) { sincos
 #else
 static inline void fast_sincos(float arg, float* s, float* c) { *s = sinf(arg); *c = cosf(arg); }
 #endif
-
-// bitwise select: a where the mask bit is set, b elsewhere (one LOP3)
-KOB_RD uint32_t bit_select(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
 
 // cos / sin (j theta) of the direction (ux, uy) (any length), integer j (:170-171), and the rotation by j theta0.
 template <int JM, bool ROT>
@@ -162,16 +161,16 @@ template <int JM, bool NOISE, bool ROT, bool GEN>
 KOB_RD void cold_block(const ColdK& K, float2 gx, float2 gy, const float (&th_old)[2], const bool (&asg)[2], float2 phi2,
                        float2 tq, float2 q, float2 rq, float2& An, float2& Bn, float2& th2, float2& radd) {
     // ---- re-assigned angle (:154-167) ----
+    // With sx, sy = +-1 by the SIGN BITS of gx, gy (gy = -0 counts as negative, consistently everywhere below) and
+    // s = sx sy: w = (gy - s gx) / (gx + s gy) in [-1, 1], and the quadrant offsets (Q1 pi/4, Q2 PI_F - pi/4, Q3 PI_F + pi/4,
+    // Q4 2 PI_F - pi/4) are the bilinear form PI_F - (PI_F/2) sy + (pi/4 - PI_F/2) s: three packed instructions, no selects.
     {
-        const float2 sgx = make_float2(copysign_bits(gx.x, gy.x), copysign_bits(gx.y, gy.y));   // |gx| sign(gy) = s gx
-        const float2 sgy = make_float2(copysign_bits(gy.x, gx.x), copysign_bits(gy.y, gx.y));   // |gy| sign(gx) = s gy
-        const float2 w = f2mul(f2sub(gy, sgx), rcp2(f2add(gx, sgy)));
-        // quadrant offset by the two sign BITS (gy = -0 counts as negative, like in s above): bitwise selects, no branches
-        const uint32_t o1 = fbits(K.off1), o2 = fbits(K.off2), o3 = fbits(K.off3), o4 = fbits(K.off4);
-        const uint32_t mx0 = (uint32_t)((int)fbits(gx.x) >> 31), my0 = (uint32_t)((int)fbits(gy.x) >> 31);
-        const uint32_t mx1 = (uint32_t)((int)fbits(gx.y) >> 31), my1 = (uint32_t)((int)fbits(gy.y) >> 31);
-        const float2 off = make_float2(bitsf(bit_select(mx0, bit_select(my0, o3, o2), bit_select(my0, o4, o1))),
-                                       bitsf(bit_select(mx1, bit_select(my1, o3, o2), bit_select(my1, o4, o1))));
+        const float2 sx = make_float2(copysign_bits(1.0f, gx.x), copysign_bits(1.0f, gx.y));
+        const float2 sy = make_float2(copysign_bits(1.0f, gy.x), copysign_bits(1.0f, gy.y));
+        const float2 sxy = f2mul(sx, sy);
+        const float2 w = f2mul(f2sub(gy, f2mul(gx, sxy)), rcp2(f2fma(gy, sxy, gx)));
+        float2 off = f2fma(sy, f2(K.off_y), f2(K.off_c));
+        off = f2fma(sxy, f2(K.off_s), off);
         th2 = f2add(off, atan11_2(w));
     }
     // ---- reaction term q ((phi - 1/2) + m(T)) [+ noise] of row r-2 (:206-214) ----
@@ -187,33 +186,28 @@ KOB_RD void cold_block(const ColdK& K, float2 gx, float2 gy, const float (&th_ol
     // ---- cos / sin (j (theta - theta0)) (:170-171) from the gradient direction ----
     float2 Cc = f2(1.0f), Ss = f2(0.0f);
     if (JM >= 0) aniso_cs<JM, ROT>(K, gx, gy, Cc, Ss);
-    // ---- the rare cells: dead-band in gx (case A, :154-158: theta = +-PI_F/2, direction (0, +-1)) and held non-zero angles
-    // (direction (cos theta, sin theta) by MUFU after folding theta into [-pi, pi]) ----
+    // ---- the cells that do not take their direction from the gradient: dead-band in gx (case A, :154-158: theta =
+    // +-PI_F/2, anisotropy by two host constants) and held non-zero angles (cos / sin (j (theta - theta0)) by MUFU on the
+    // angle reduced to [-1/2, 1/2] revolutions).  Whole saturated regions consist of such cells, so this is kept cheap. ----
     {
         const bool fl0 = asg[0] && fabsf(gx.x) <= K.e, fl1 = asg[1] && fabsf(gx.y) <= K.e;
         const bool h0 = GEN && th_old[0] != 0.f, h1 = GEN && th_old[1] != 0.f;
         if (KOB_ANY(fl0 || fl1 || h0 || h1)) {
-            float2 ux = gx, uy = gy;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const bool fl = k ? fl1 : fl0, held = k ? h1 : h0;
-                const float gyk = k ? gy.y : gy.x;
-                const float sg = gyk < 0.f ? -1.0f : 1.0f;
-                float t = th_old[k];
-                if (GEN) t = t > 3.14159265358979f ? fmaf(-1.0f, 6.28318548202514648f, t) + 1.74845553e-7f : t;   // - 2 pi (hi, lo)
-                const float ct = GEN ? fast_cos(t) : 0.f, st = GEN ? fast_sin(t) : 0.f;
+                const bool neg = (k ? gy.y : gy.x) < 0.f;
                 float& thk = k ? th2.y : th2.x;
-                float& uxk = k ? ux.y : ux.x;
-                float& uyk = k ? uy.y : uy.x;
-                thk = fl ? sg * K.half_pi : thk;
-                uxk = fl ? 0.0f : (held ? ct : uxk);
-                uyk = fl ? sg : (held ? st : uyk);
-            }
-            if (JM >= 0) {
-                float2 C2, S2;
-                aniso_cs<JM, ROT>(K, ux, uy, C2, S2);
-                if (fl0 || h0) { Cc.x = C2.x; Ss.x = S2.x; }
-                if (fl1 || h1) { Cc.y = C2.y; Ss.y = S2.y; }
+                float& Ck = k ? Cc.y : Cc.x;
+                float& Sk = k ? Ss.y : Ss.x;
+                thk = fl ? (neg ? -K.half_pi : K.half_pi) : thk;
+                if (JM >= 0) {
+                    float u = fmaf(th_old[k], K.j_rev, K.jth0_rev);
+                    u = (u - rintf(u)) * 6.28318530717958648f;
+                    const float ch = GEN ? fast_cos(u) : 0.f, sh = GEN ? fast_sin(u) : 0.f;
+                    Ck = fl ? (neg ? K.cfl_m : K.cfl_p) : (held ? ch : Ck);
+                    Sk = fl ? (neg ? K.sfl_m : K.sfl_p) : (held ? sh : Sk);
+                }
             }
         }
     }
@@ -231,6 +225,33 @@ KOB_RD void cold_block(const ColdK& K, float2 gx, float2 gy, const float (&th_ol
     float2 ep = f2fma(Cc, f2(K.ebd), f2(K.epsbar));                                             // :170
     float2 ed = f2mul(Ss, f2(K.neg_ebjd));                                                      // :171
     const bool d0 = !asg[0] && !(GEN && th_old[0] != 0.f), d1 = !asg[1] && !(GEN && th_old[1] != 0.f);   // holds theta = 0
+    ep = make_float2(d0 ? K.eps0 : ep.x, d1 ? K.eps0 : ep.y);
+    ed = make_float2(d0 ? K.epsd0 : ed.x, d1 ? K.epsd0 : ed.y);
+    An = f2mul(ep, ep);
+    Bn = f2mul(ep, ed);
+}
+
+// eps^2 and eps eps' of two cells that HOLD their angle (no re-assignment anywhere in the warp's row): the same operations the
+// data-dependent block performs for such cells.
+template <int JM, bool ROT>
+KOB_RD void held_block(const ColdK& K, const float (&th_old)[2], float2& An, float2& Bn) {
+    float2 Cc = f2(1.0f), Ss = f2(0.0f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float& Ck = k ? Cc.y : Cc.x;
+        float& Sk = k ? Ss.y : Ss.x;
+        if (JM >= 0) {
+            float u = fmaf(th_old[k], K.j_rev, K.jth0_rev);
+            u = (u - rintf(u)) * 6.28318530717958648f;
+            Ck = fast_cos(u);
+            Sk = fast_sin(u);
+        } else if (th_old[k] != 0.f) {
+            fast_sincos(K.aniso * (th_old[k] - K.theta0), &Sk, &Ck);
+        }
+    }
+    float2 ep = f2fma(Cc, f2(K.ebd), f2(K.epsbar));
+    float2 ed = f2mul(Ss, f2(K.neg_ebjd));
+    const bool d0 = th_old[0] == 0.f, d1 = th_old[1] == 0.f;                                    // holds theta = 0
     ep = make_float2(d0 ? K.eps0 : ep.x, d1 ? K.eps0 : ep.y);
     ed = make_float2(d0 ? K.epsd0 : ed.x, d1 ? K.epsd0 : ed.y);
     An = f2mul(ep, ep);
@@ -277,10 +298,7 @@ __device__ __forceinline__ float2 row_tonly(RowState& S, const RowConst& C, floa
 // row r-1 keeps if the state machine holds it (GEN only), draw() = noise draw r - 1/2 for the two cells of row r-2 (called
 // only when the data-dependent block runs).  Outputs: phi+/T+ of row r-2; asg / th2 = which cells of row r-1 re-assign their
 // angle, and to what (th2 is valid only where asg).  Returns the warp vote "some cell did data-dependent work".
-// DENSE: run the data-dependent block without asking (the caller predicts it from the previous rows; always correct, only
-// slower on far-field rows) — the row is then one straight-line region, which is what lets the scheduler overlap the two
-// atan chains, the Philox rounds and the stencil arithmetic.
-template <int JM, bool NOISE, bool ROT, bool GEN, bool DENSE, class Draw>
+template <int JM, bool NOISE, bool ROT, bool GEN, class Draw>
 __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const ColdK& K, float2 pn, float w, float ee, float2 tn,
                                          float tw, float te, const float (&th_old_in)[2], Draw&& draw, float2& np_, float2& nt_,
                                          float2& th2, bool (&asg)[2]) {
@@ -300,13 +318,14 @@ __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const C
     float2 radd = f2(0.f);
     asg[0] = (S.gx1.x < -K.e) || (fabsf(gyn.x) > K.e);                                        // :154-167: theta re-assigned
     asg[1] = (S.gx1.y < -K.e) || (fabsf(gyn.y) > K.e);
-    bool vote = true;
-    if (!DENSE) {
-        bool interesting = asg[0] || asg[1] || q.x != 0.f || q.y != 0.f;
-        if (GEN) interesting |= th_old_in[0] != 0.f || th_old_in[1] != 0.f;                   // a held cell may carry an angle
-        vote = __any_sync(0xffffffffu, interesting);
-    }
-    if (DENSE || vote) {
+    // Votes: `busy` = some cell re-assigns its angle or has phi (1 - phi) != 0 -> the whole data-dependent block; otherwise,
+    // `held` = some cell carries a non-zero held angle (the inside of a saturated region: phi == 1 exactly, gradient in the
+    // dead-band) -> only eps(theta) of those cells is evaluated; otherwise the far-field constants above stand.  A cell gets the
+    // same bits whichever tier its row takes (the skipped terms are exact zeros), so the tiers — which depend on what the
+    // OTHER lanes of the warp hold — never show in the results.
+    const bool busy = __any_sync(0xffffffffu, asg[0] || asg[1] || q.x != 0.f || q.y != 0.f);
+    bool vote = busy;
+    if (busy) {
         float th_old[2];
         th_old[0] = (GEN && !asg[0]) ? th_old_in[0] : 0.f;
         th_old[1] = (GEN && !asg[1]) ? th_old_in[1] : 0.f;
@@ -316,6 +335,15 @@ __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const C
         cold_block<JM, NOISE, ROT, GEN>(K, S.gx1, gyn, th_old, asg, S.po0, S.tq1, q, rq, An, Bn, th2, radd);
         Pn = f2mul(Bn, S.gx1);
         Qn = f2mul(Bn, gyn);
+    } else if (GEN) {
+        const bool held = __any_sync(0xffffffffu, th_old_in[0] != 0.f || th_old_in[1] != 0.f);
+        if (held) {
+            float2 Bn;
+            held_block<JM, ROT>(K, th_old_in, An, Bn);
+            Pn = f2mul(Bn, S.gx1);
+            Qn = f2mul(Bn, gyn);
+            vote = true;
+        }
     }
     // ---- pass 2 for row r-2 ----
     const float2 dA = make_float2(S.A2.y - A_w, A_e - S.A2.x);                                // :190-192

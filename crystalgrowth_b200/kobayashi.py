@@ -180,9 +180,38 @@ class Kobayashi:
         self._ck(self._L.kob_set_fields(self._h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]))
         self.sync()
 
+    def window(self, x0: int, y0: int, w: int, h: int, phi=True, t=True, angl=True):
+        """(phi, T, theta) of the w x h window at (x0, y0): what a viewer of a huge torus reads (kob_get_window)."""
+        out = [np.empty((h, w), self.dtype) if want else None for want in (phi, t, angl)]
+        self._ck(self._L.kob_get_window(self._h, x0, y0, w, h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in out]))
+        return tuple(out)
+
+    def set_window(self, x0: int, y0: int, phi=None, t=None, angl=None):
+        """Write a window (all given arrays must have the same (h, w) shape); the rest of the field is kept."""
+        arrs = [None if a is None else np.ascontiguousarray(a, self.dtype) for a in (phi, t, angl)]
+        shapes = {a.shape for a in arrs if a is not None}
+        if len(shapes) != 1:
+            raise ValueError("window arrays must share one (h, w) shape")
+        h, w = shapes.pop()
+        self._ck(self._L.kob_set_window(self._h, x0, y0, w, h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]))
+        self.sync()
+
     def get_fields_into(self, phi_ptr, t_ptr, angl_ptr):
         """Raw-pointer variant (pinned host buffers) used by the end-to-end benchmark."""
         self._ck(self._L.kob_get_fields(self._h, phi_ptr, t_ptr, angl_ptr))
+
+    def get_fields_async(self, phi_ptr, t_ptr, angl_ptr):
+        """Snapshot now, copy to the (pinned) host buffers on a second stream while stepping continues; wait_fields() joins."""
+        self._ck(self._L.kob_get_fields_async(self._h, phi_ptr, t_ptr, angl_ptr))
+
+    def wait_fields(self):
+        self._ck(self._L.kob_wait_fields(self._h))
+
+    def host_alloc_near(self, nbytes: int) -> C.c_void_p:
+        """Pinned host memory on the NUMA node of this context's GPU."""
+        p = C.c_void_p()
+        self._ck(self._L.kob_host_alloc_near(self._h, C.byref(p), nbytes))
+        return p
 
     def set_fields_from(self, phi_ptr, t_ptr, angl_ptr):
         self._ck(self._L.kob_set_fields(self._h, phi_ptr, t_ptr, angl_ptr))
@@ -280,3 +309,7 @@ class Kobayashi:
 
     def halo_refresh(self):
         self._ck(self._L.kob_halo_refresh(self._h))
+
+    def ring_join(self, name: str, rank: int, world: int):
+        """Ring-wide adaptive step path inside the library (kob_ring_join): every strip of the ring joins under one name."""
+        self._ck(self._L.kob_ring_join(self._h, name.encode(), rank, world))

@@ -85,6 +85,10 @@ public:
     template <typename real> std::vector<real> angl() { return field<real>(2); }
     void getFields(void* phi, void* t, void* angl) { ck(kob_get_fields(ctx_, phi, t, angl), "kob_get_fields"); }
     void setFields(const void* phi, const void* t, const void* angl) { ck(kob_set_fields(ctx_, phi, t, angl), "kob_set_fields"); }
+    void getFieldsAsync(void* phi, void* t, void* angl) { ck(kob_get_fields_async(ctx_, phi, t, angl), "kob_get_fields_async"); }
+    void waitFields() { ck(kob_wait_fields(ctx_), "kob_wait_fields"); }
+    void getWindow(int64_t x0, int64_t y0, int64_t w, int64_t h, void* phi, void* t, void* angl) { ck(kob_get_window(ctx_, x0, y0, w, h, phi, t, angl), "kob_get_window"); }
+    void setWindow(int64_t x0, int64_t y0, int64_t w, int64_t h, const void* phi, const void* t, const void* angl) { ck(kob_set_window(ctx_, x0, y0, w, h, phi, t, angl), "kob_set_window"); }
     void setNoiseField(const float* r) { ck(kob_set_noise_field(ctx_, r), "kob_set_noise_field"); }
     std::vector<uint8_t> renderRGBA() {
         std::vector<uint8_t> img(4u * static_cast<size_t>(nx_) * static_cast<size_t>(ny_));

@@ -140,6 +140,18 @@ int kob_sync(kob_ctx* ctx);
  * the call returns). */
 int kob_get_fields(kob_ctx* ctx, void* phi, void* t, void* angl);
 int kob_set_fields(kob_ctx* ctx, const void* phi, const void* t, const void* angl);
+/* Asynchronous readback: the current arrays are snapshotted on the device (ordered with the steps queued so far) and copied to
+ * the host buffers on a second stream while kob_step / kob_update continue; kob_wait_fields returns when the last
+ * kob_get_fields_async has landed.  One readback in flight per context (a second call waits for the first).  Use pinned
+ * buffers (kob_host_alloc / kob_host_alloc_near).  This is how a viewer overlaps frame n's picture with frame n+1's steps. */
+int kob_get_fields_async(kob_ctx* ctx, void* phi, void* t, void* angl);
+int kob_wait_fields(kob_ctx* ctx);
+/* The same for the w x h window whose lower-left cell is (x0, y0) (local rows; no wrap): buffers hold w*h elements, row
+ * stride w.  What a viewer of a 65536^2 torus reads, and how state beyond 2^31 cells is inspected — the reference's `int`
+ * index (src/Kobayashi.h:91) cannot address such grids at all.  kob_set_window is asynchronous like kob_set_fields and
+ * refreshes the periodic aliases of the cells it touches. */
+int kob_get_window(kob_ctx* ctx, int64_t x0, int64_t y0, int64_t w, int64_t h, void* phi, void* t, void* angl);
+int kob_set_window(kob_ctx* ctx, int64_t x0, int64_t y0, int64_t w, int64_t h, const void* phi, const void* t, const void* angl);
 /* Host-injected noise field r in [0,1) (nx*ny floats, reference layout) used instead of the Philox
  * stream on every following step; NULL returns to Philox.  Parity aid named by the north star. */
 int kob_set_noise_field(kob_ctx* ctx, const float* r);
@@ -174,6 +186,9 @@ int kob_abi_version(void);
 /* Pinned host memory for the end-to-end (host buffer) path. */
 int kob_host_alloc(void** p, size_t bytes);
 int kob_host_free(void* p);
+/* Pinned host memory on the NUMA node of the context's GPU (falls back to kob_host_alloc where the topology is not exposed):
+ * with one process per GPU on a two-socket box this keeps every rank's PCIe copies off the inter-socket link. */
+int kob_host_alloc_near(kob_ctx* ctx, void** p, size_t bytes);
 
 /* ---- row strips (multi-GPU) ------------------------------------------------------ */
 
@@ -185,6 +200,13 @@ int kob_ipc_export(kob_ctx* ctx, kob_ipc_handle* out);
 int kob_ipc_link(kob_ctx* ctx, const kob_ipc_handle* lower, const kob_ipc_handle* upper);
 /* Same-process variant (strips on one GPU, or peer-enabled GPUs of one process). */
 int kob_link_local(kob_ctx* ctx, kob_ctx* lower, kob_ctx* upper);
+/* Ring-wide adaptive step path without help from the caller.  Linked strips must all run the same launch sequence, so the
+ * per-context adaptive choice between the single-step kernel and two-step launch pairs is off inside a ring.  After every
+ * strip (one process / thread each) has called kob_ring_join with the same `name` (unique per ring on this host, <= 47 chars),
+ * its `rank` and the ring size, kob_step agrees on the path across the ring every 64 sub-steps through a small POSIX
+ * shared-memory segment: the maximum of the strips' density probes, with hysteresis — every strip switches on the same
+ * sub-step.  All strips must be stepped by the same amounts (they must anyway).  Results never depend on the path. */
+int kob_ring_join(kob_ctx* ctx, const char* name, int32_t rank, int32_t world);
 /* Push this strip's current boundary rows into the linked neighbours' ghost rows (after kob_set_fields /
  * kob_reset / kob_add_nucleus on a linked strip).  Collective in spirit: call on every strip, then kob_sync. */
 int kob_halo_refresh(kob_ctx* ctx);

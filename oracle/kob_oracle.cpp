@@ -62,6 +62,7 @@ struct OracleBase {
     virtual void set_ghost(int side, const void* phi2, const void* t2, const void* angl2) = 0;
     int prec = 32, math = MATH_LIBM, threads = 1;
     int64_t nx = 0, ny = 0, ny_global = 0, y0 = 0;
+    int64_t noise_x0 = 0, noise_y0 = 0;   // global cell of local (0, 0) for the Philox keys: a window of a larger torus
     kob_params p{};
     uint64_t seed = 0, step_counter = 0;
     bool self_periodic = true;
@@ -178,7 +179,7 @@ struct Oracle : OracleBase {
             if (noisy) {
                 const int64_t jl = jp - G;
                 const float r = noise_field.empty()
-                                    ? kob::noise_r(seed, step_counter, (uint32_t)i, (uint32_t)(y0 + jl))
+                                    ? kob::noise_r(seed, step_counter, (uint32_t)(noise_x0 + i), (uint32_t)(noise_y0 + y0 + jl))
                                     : noise_field[(size_t)i + (size_t)nx * (size_t)jl];
                 sum = sum + (noise_a * q) * ((real)r - (real)0.5f);
             }
@@ -283,6 +284,9 @@ void kobo_set_noise_field(void* h, const float* r) {
 void kobo_set_step_counter(void* h, uint64_t s) { static_cast<OracleBase*>(h)->step_counter = s; }
 uint64_t kobo_get_step_counter(void* h) { return static_cast<OracleBase*>(h)->step_counter; }
 void kobo_set_threads(void* h, int n) { static_cast<OracleBase*>(h)->threads = n < 1 ? 1 : n; }
+// The oracle grid is a WINDOW of a larger torus: local cell (0, 0) is global cell (x0, y0) for the Philox noise keys
+// (full-size parity tests compare a window of a 16384^2 GPU run with a 250^2 oracle run).
+void kobo_set_noise_origin(void* h, int64_t x0, int64_t y0) { OracleBase* o = static_cast<OracleBase*>(h); o->noise_x0 = x0; o->noise_y0 = y0; }
 int kobo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
             "kobo_set_noise_field": [C.c_void_p, C.c_void_p],
             "kobo_set_step_counter": [C.c_void_p, C.c_uint64],
             "kobo_set_threads": [C.c_void_p, C.c_int],
+            "kobo_set_noise_origin": [C.c_void_p, C.c_int64, C.c_int64],
             "kobo_philox": [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
         }.items():
             getattr(L, name).restype = None
@@ -122,6 +123,7 @@ class Oracle:
     def add_nucleus(self, x, y): lib().kobo_add_nucleus(self._h, x, y)
     def step(self, n=1): lib().kobo_step(self._h, n)
     def set_threads(self, n): lib().kobo_set_threads(self._h, n)
+    def set_noise_origin(self, x0, y0): lib().kobo_set_noise_origin(self._h, int(x0), int(y0))
 
     def set_params(self, params):
         self.params = params

@@ -24,8 +24,13 @@ static ColdK make_k(const Prm& p) {
     ColdK K{};
     K.e = FLT_EPSILON;
     const double q = 0.78539816339744830962;
-    K.off1 = (float)q; K.off2 = (float)((double)PI_F - q); K.off3 = (float)((double)PI_F + q); K.off4 = (float)(2.0 * (double)PI_F - q);
+    K.off_c = PI_F; K.off_y = -0.5f * PI_F; K.off_s = (float)(q - 0.5 * (double)PI_F);
     K.half_pi = 0.5f * PI_F;
+    {   // case A cells: the reference evaluates cos / sin (j * angl) with angl = +-0.5f * PI_F in float (:156-158, :170-171)
+        const float ap = p.aniso * (0.5f * PI_F - p.theta0), am = p.aniso * (-0.5f * PI_F - p.theta0);
+        K.cfl_p = std::cos(ap); K.sfl_p = std::sin(ap); K.cfl_m = std::cos(am); K.sfl_m = std::sin(am);
+        K.j_rev = (float)((double)p.aniso / 6.283185307179586); K.jth0_rev = (float)(-(double)p.aniso * p.theta0 / 6.283185307179586);
+    }
     K.ebd = p.epsbar * p.delta; K.epsbar = p.epsbar;
     K.neg_ebjd = ((-p.epsbar) * p.aniso) * p.delta;
     const double a0 = (double)p.aniso * (0.0 - (double)p.theta0);
