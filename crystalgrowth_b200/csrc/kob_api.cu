@@ -131,6 +131,7 @@ struct kob_ctx {
     unsigned int* h_count = nullptr;   // pinned: work-list length of the last probed launch pair
     cudaEvent_t ev_count = nullptr;
     bool count_pending = false;
+    uint64_t probe_launch = 0;         // launch count at which the pending probe was issued
     long long count_total = 1;
     double general_frac = 0.0;
     bool single_mode = false;          // adaptive policy: the field is dense, use the single-step kernel
@@ -278,7 +279,7 @@ int kernel_occupancy(kob_ctx* c, const void* kern, int threads, int smem, int* o
 }
 
 // Rows per job: the configured height or a shorter one (halvings down to 4) — whichever minimises the expected makespan of the
-// dynamically scheduled queue, (total rows incl. warm-up rows) / warps + one job (the last one to finish).  On big grids that is
+// dynamically scheduled queue, (total rows incl. warm-up rows and per-job overhead) / warps + one job (the last one to finish).  On big grids that is
 // the configured height; on small ones the jobs shrink until the tail is short and every warp of the persistent grid has work.
 // Not applied when the height was set explicitly (environment).  Bit-neutral, like every job knob.
 int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps, int warm) {
@@ -287,7 +288,8 @@ int auto_job_rows(int yj, bool fixed, int nstrips, long long ny, long long warps
     double best_cost = -1.0;
     for (int h = yj; h >= 4; h /= 2) {
         const long long jobs = (long long)nstrips * ((ny + h - 1) / h);
-        const double cost = (double)jobs * (h + warm) / (double)warps + (double)(h + warm);
+        const double per_job = (double)(h + warm) + 8.0;          // + claim, theta-flag scan and TMA ring fill: about 8 rows' worth
+        const double cost = (double)jobs * per_job / (double)warps + per_job;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = h; }
     }
     return std::max(4, best / 4 * 4);
@@ -337,6 +339,7 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         KOB_CUDA(c, cudaMemcpyAsync(c->h_count, live_ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
         KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
         c->count_pending = true;
+        c->probe_launch = c->launches;
         c->count_total = (long long)f.nstrips * f.nseg;
     }
     c->job_expected += (unsigned long long)njobs + (unsigned long long)grid * FAST_WARPS;   // every warp overshoots once
@@ -448,6 +451,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
             KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
             KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
             c->count_pending = true;
+        c->probe_launch = c->launches;
             c->count_total = (long long)F2_RANGES * f.nstrips * f.nseg;
         }
         return KOB_OK;
@@ -794,6 +798,11 @@ int kob_step(kob_ctx* c, int64_t nsteps) {
     KOB_TRY(set_device(c));
     const bool ring = c->ring != nullptr && c->linked && c->fast2 == 2 && c->kernel == KOB_KERNEL_FAST;
     for (int64_t s = 0; s < nsteps;) {
+        // Launches are queued far ahead of the GPU, and the density probe that steers the adaptive path comes back
+        // asynchronously: without a bound, one long kob_step call would run entirely on the path chosen before it.  So the host
+        // never runs more than 16 launches ahead of an outstanding probe (the GPU still has those 16 queued: no bubble).
+        if (c->count_pending && c->fast2 == 2 && !c->linked && c->launches - c->probe_launch >= 16)
+            KOB_CUDA(c, cudaEventSynchronize(c->ev_count));
         poll_density_probe(c);
         // KOB_FAST2 / kob_set_path_mode: 0 = single-step kernel, 1 = pairs, 2 = adaptive.  Linked strips must all run the same
         // launch sequence: "adaptive" there means pairs, unless the ring agrees on a mode — through kob_ring_join (below), or

@@ -59,7 +59,14 @@ __global__ void kob_rebuild_flags(const real* __restrict__ theta, uint32_t* __re
         if (xp < pitch && yp < rows && theta[yp * pitch + xp] != (real)0) any = 1;
     }
     any = __syncthreads_or(any);
-    if (threadIdx.x == 0) tflags[by * nfbx + bx] = any ? 1u : 0u;
+    // Blocks that contain ghost rows are only ever SET here: a linked neighbour's alias refresh may be setting the same flag
+    // at this very moment (its theta rows land in my ghost rows), and clearing it after that store would leave held angles
+    // unseen.  A stale set flag is just a conservative hint.
+    const bool ghost_block = by * FBY < GY || (long long)(by + 1) * FBY > rows - GY;
+    if (threadIdx.x == 0) {
+        if (any) tflags[by * nfbx + bx] = 1u;
+        else if (!ghost_block) tflags[by * nfbx + bx] = 0u;
+    }
 }
 
 // _createNucleus (src/Kobayashi.cpp:116-123) at GLOBAL cell (x, y), periodic wrap, this strip's share only.

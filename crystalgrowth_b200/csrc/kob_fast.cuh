@@ -195,7 +195,7 @@ __device__ __forceinline__ void fast_seam_done(const StepArgs<float>& a, const F
 
 // ---- shared-memory plan of one warp of kob_step_fast (FAST_WARP_REGION bytes) ------------------------------------------------
 // Two layouts over the same bytes; a job uses one of them from its first TMA load to its last TMA store:
-//   ring 0 (lean and seam jobs):  4 input stages [phi box | T box]              + 2 output buffers [phi+ | T+]
+//   ring 0 (lean and seam jobs):  4 input stages [phi box | T box]; results leave by coalesced 8-byte stores from registers
 //   ring 1 (live jobs)         :  3 input stages [phi box | T box | theta box]  + 1 output buffer  [phi+ | T+ | theta]
 // Input boxes are 4 rows x 68 columns (they must start on a 16-byte boundary in global memory: box column 0 is cell
 // 60*strip - 4), output boxes 4 rows x 60 columns, each padded to a multiple of 128 bytes (TMA shared-memory alignment).  The lean path is HBM bound and wants the deep ring; live jobs are issue bound and want the
@@ -204,7 +204,7 @@ constexpr int FAST_OUTC = FastGeom::OUTC;
 constexpr int FAST_OBOX_BYTES = (FAST_RB * FAST_OUTC * 4 + 127) / 128 * 128;           // 1024
 constexpr int FAST_BOX_BYTES = FAST_BOX_FLOATS * 4;                                    // 1152
 constexpr int FAST_R0_NST = 4, FAST_R1_NST = 3;
-constexpr int FAST_R0_NOBUF = 2, FAST_R1_NOBUF = 1;   // output buffers (ring 1: the store of chunk c has been read by the time chunk c+1 writes)
+constexpr int FAST_R0_NOBUF = 0, FAST_R1_NOBUF = 1;   // output buffers (ring 1: the store of chunk c has been read by the time chunk c+1 writes)
 constexpr int FAST_R0_STAGE = 2 * FAST_BOX_BYTES, FAST_R1_STAGE = 3 * FAST_BOX_BYTES;
 constexpr int FAST_R0_OUT = FAST_R0_NST * FAST_R0_STAGE, FAST_R1_OUT = FAST_R1_NST * FAST_R1_STAGE;
 constexpr int FAST_R0_OBUF = 2 * FAST_OBOX_BYTES, FAST_R1_OBUF = 3 * FAST_OBOX_BYTES;
@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
             constexpr bool GEN = MODE == 1;
             constexpr int NST = GEN ? FAST_R1_NST : FAST_R0_NST, STAGE = GEN ? FAST_R1_STAGE : FAST_R0_STAGE;
             constexpr int OUT0 = GEN ? FAST_R1_OUT : FAST_R0_OUT, OBUF = GEN ? FAST_R1_OBUF : FAST_R0_OBUF;
-            constexpr int NOBUF = GEN ? FAST_R1_NOBUF : FAST_R0_NOBUF;
             uint64_t* bars = GEN ? bars1 : bars0;
             unsigned int& gchunk = GEN ? gch1 : gch0;
             auto issue = [&](int c) {                    // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
@@ -405,6 +404,10 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
             bool prevz = false;                          // !GEN: the previous chunk's phi rows were all +0
             float2 th_hold = f2(0.f);                    // GEN: angle of the row produced by the last iteration of the previous chunk
             const int lane_out = (lane - 1) * CPL * 4;   // byte offset of this lane's pair in an output row (mid lanes)
+            // !GEN: running pointers to cell (x, r-2) of the output arrays (coalesced 8-byte stores straight from registers)
+            const long long o2 = pidx<float>(pitch, x, y0 - 4);
+            float* pphi = phi_out + o2;
+            float* ptt = t_out + o2;
 
             for (int c = 0; c < nch; ++c) {
                 const unsigned int gi = gchunk + (unsigned int)c;
@@ -415,10 +418,10 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                 const float* sp = reinterpret_cast<const float*>(stage) + CPL * lane + CPL;   // this lane's own phi cells
                 const float* stt = sp + FAST_BOX_FLOATS;                            // T rows (one row behind)
                 const float* sth = stt + FAST_BOX_FLOATS;                           // GEN: theta rows (same rows as T)
-                unsigned char* obuf = region + OUT0 + (NOBUF == 2 ? (c & 1) : 0) * OBUF;   // output boxes of this chunk
+                unsigned char* obuf = region + OUT0;                                // GEN: output boxes of this chunk
                 const bool store = c > 0;                                           // chunk 0 only warms the windows up
                 const int yrel0 = c * RB - 4;                                       // (r - 2) - y0 for rr = 0
-                if (NOBUF == 1 && c > 1) {               // single output buffer: the previous chunk's boxes must have been read
+                if (GEN && c > 1) {                      // single output buffer: the previous chunk's boxes must have been read
                     if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                 }
@@ -440,16 +443,21 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                         for (int rr = 0; rr < RB; ++rr) {
                             const float* trow = stt + rr * BW;
                             const float2 nt_ = row_tonly(S, f.rc, *reinterpret_cast<const float2*>(trow), trow[-1], trow[CPL]);
-                            if (store && mid_lane) {
-                                *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = f2(0.f);
-                                *reinterpret_cast<float2*>(obuf + FAST_OBOX_BYTES + rr * (OUTC * 4) + lane_out) = nt_;
+                            if ((unsigned int)(yrel0 + rr) < nstore) {
+                                *reinterpret_cast<float2*>(pphi) = f2(0.f);
+                                *reinterpret_cast<float2*>(ptt) = nt_;
                             }
+                            pphi += pitch;
+                            ptt += pitch;
                         }
                     }
                 }
                 if (!skipped) {
+                    // (the chunk is unrolled whole: a loop over row pairs halves the code — and the instruction-fetch stalls that
+                    // small grids with short jobs show — but ptxas then spends ~50 register moves per row at the back edge)
 #pragma unroll
                     for (int rr = 0; rr < RB; ++rr) {
+                        const int ro = rr & 1;
                         const unsigned int yrel = (unsigned int)(yrel0 + rr);       // row of pass 2, relative to y0
                         const float* prow = sp + rr * BW;
                         const float* trow = stt + rr * BW;
@@ -470,14 +478,25 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                                 rq.y = (yrel < nvalid ? __ldg(&a.noise_field[(long long)(x + 1) + (long long)a.nx * y]) : 0.5f) - 0.5f;
                                 return rq;
                             }
-                            return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, (rr & 1) == 0, lane);
+                            return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, ro == 0, lane);
                         };
-                        if ((rr & 1) == 0) S.have_next = false;
-                        const bool vote = row_full<JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
-                                                                               th_in, draw, np_, nt_, th2, asg);
-                        if (store && mid_lane) {
-                            *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = np_;
-                            *reinterpret_cast<float2*>(obuf + FAST_OBOX_BYTES + rr * (OUTC * 4) + lane_out) = nt_;
+                        if (ro == 0) S.have_next = false;
+                        const bool vote = ro == 0 ? row_full<0, JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                                          th_in, draw, np_, nt_, th2, asg)
+                                                  : row_full<1, JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                                          th_in, draw, np_, nt_, th2, asg);
+                        if (GEN) {
+                            if (store && mid_lane) {
+                                *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = np_;
+                                *reinterpret_cast<float2*>(obuf + FAST_OBOX_BYTES + rr * (OUTC * 4) + lane_out) = nt_;
+                            }
+                        } else {
+                            if (yrel < nstore) {
+                                *reinterpret_cast<float2*>(pphi) = np_;
+                                *reinterpret_cast<float2*>(ptt) = nt_;
+                            }
+                            pphi += pitch;
+                            ptt += pitch;
                         }
                         if (GEN) {
                             // angle of row r-1 after this step: re-assigned or kept.  Rows are written back whole (a held cell gets
@@ -499,25 +518,26 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                         }
                     }
                 }
-                // ---- this chunk's output boxes leave by TMA; the next chunk's input is requested ----
-                if (store) fence_async_smem();
+                // ---- live jobs: this chunk's output boxes leave by TMA; the next chunk's input is requested ----
+                if (GEN && store) fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (store) {
+                    if (GEN && store) {
                         const int ox = strip * OUTC + GX, oy = y0 + (c - 1) * RB + GY;
                         tma_store_2d(omap_phi, ox, oy, obuf);
                         tma_store_2d(omap_t, ox, oy, obuf + FAST_OBOX_BYTES);
-                        if (GEN) tma_store_2d(omap_th, ox, oy, obuf + 2 * FAST_OBOX_BYTES);
+                        tma_store_2d(omap_th, ox, oy, obuf + 2 * FAST_OBOX_BYTES);
                         tma_store_commit();
-                        if (NOBUF == 2) tma_store_wait_read<1>();   // the other buffer (chunk c-1's boxes) has been read: free for chunk c+1
                     }
                     if (c + NST < nch) issue(c + NST);
                 }
-                __syncwarp();
+                if (GEN) __syncwarp();
             }
             gchunk += (unsigned int)nch;
-            if (lane == 0) tma_store_wait_read<0>();     // the next job may lay the region out differently
-            __syncwarp();
+            if (GEN) {
+                if (lane == 0) tma_store_wait_read<0>();     // the next job may lay the region out differently
+                __syncwarp();
+            }
         };
 
         // ---- seam jobs (MODE 2): the ragged right edge, the alias stores to ghost columns / neighbour strips, arbitrary job
@@ -580,8 +600,10 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                         return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, (rr & 1) == 0, lane);
                     };
                     if ((rr & 1) == 0) S.have_next = false;
-                    const bool vote = row_full<JM, NOISE != 0, ROT, true>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
-                                                                            thp0, draw, np_, nt_, th2, asg);
+                    const bool vote = (rr & 1) == 0 ? row_full<0, JM, NOISE != 0, ROT, true>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                                               thp0, draw, np_, nt_, th2, asg)
+                                                    : row_full<1, JM, NOISE != 0, ROT, true>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                                               thp0, draw, np_, nt_, th2, asg);
                     // ---- store the re-assigned angles of owned cells of row r-1 ----
                     if (vote && yrel + 1u < nstore) {
 #pragma unroll

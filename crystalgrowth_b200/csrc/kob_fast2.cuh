@@ -75,7 +75,9 @@ __device__ __forceinline__ void f2_row(RowState& S, const FastArgs& f, float2 pn
     if (even) S.have_next = false;
     bool asg[2];
     float2 th2;
-    row_full<JM, NOISE, ROT, GEN>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
+    // `even` is a compile-time fact after the callers' row loops are unrolled: the branch folds away
+    if (even) row_full<0, JM, NOISE, ROT, GEN>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
+    else row_full<1, JM, NOISE, ROT, GEN>(S, f.rc, f.ck, pn, w, ee, tn, tw, te, th_old_in, draw, np_, nt_, th2, asg);
     th_eff[0] = asg[0] ? th2.x : (GEN ? th_old_in[0] : 0.f);
     th_eff[1] = asg[1] ? th2.y : (GEN ? th_old_in[1] : 0.f);
     any_asg |= asg[0] || asg[1];

@@ -261,17 +261,22 @@ KOB_RD void held_block(const ColdK& K, const float (&th_old)[2], float2& An, flo
 #if defined(__CUDACC__) && !defined(KOB_HOST_EMU)
 // ---- the marching warp's register windows and the row update (device only) ------------------------------------------------
 
-// Register windows of one sub-step level; "r" is the phi row consumed in the current iteration.
+// Register windows of one sub-step level; "r" is the phi row consumed in the current iteration.  The depth-2 windows are
+// indexed by the PARITY of the iteration instead of being rotated (slot [p] holds the older row, is read, and is then
+// overwritten with the new row): a loop over row PAIRS ends with every value in the register it started in, so the row
+// loop needs neither full unrolling nor register moves.
 struct RowState {
-    float2 po0, po1;            // phi rows r-2, r-1
-    float2 gx1, gx2, gy2;       // gx(r-1); gx, gy (r-2)
+    float2 po[2];               // phi rows r-2 ([p]), r-1 ([p^1])
+    float2 gxw[2];              // gx of rows r-2 ([p]), r-1 ([p^1])
+    float2 gy2;                 // gy(r-2)
     float2 u1, lp1, lap2;       // u(r-1), c(r-1)+u(r-2), complete 9-point sum of row r-2
     float2 tq1, tu1, tlp1;      // T(r-2), u_T(r-2), c_T(r-2)+u_T(r-3)      [T lags phi by a row]
-    float2 A2, A3, P2, P3, Q2;  // eps^2 (r-2, r-3), eps*eps'*gx (r-2, r-3), eps*eps'*gy (r-2)
+    float2 A[2], P[2];          // eps^2 and eps*eps'*gx of rows r-3 ([p]), r-2 ([p^1])
+    float2 Q2;                  // eps*eps'*gy (r-2)
     uint32_t nxa, nxb;          // Philox words of the odd row, drawn at the even row
     bool have_next;
     __device__ __forceinline__ void clear() {
-        po0 = po1 = gx1 = gx2 = gy2 = u1 = lp1 = lap2 = tq1 = tu1 = tlp1 = A2 = A3 = P2 = P3 = Q2 = make_float2(0.f, 0.f);
+        po[0] = po[1] = gxw[0] = gxw[1] = gy2 = u1 = lp1 = lap2 = tq1 = tu1 = tlp1 = A[0] = A[1] = P[0] = P[1] = Q2 = make_float2(0.f, 0.f);
         nxa = nxb = 0u; have_next = false;
     }
 };
@@ -298,13 +303,15 @@ __device__ __forceinline__ float2 row_tonly(RowState& S, const RowConst& C, floa
 // row r-1 keeps if the state machine holds it (GEN only), draw() = noise draw r - 1/2 for the two cells of row r-2 (called
 // only when the data-dependent block runs).  Outputs: phi+/T+ of row r-2; asg / th2 = which cells of row r-1 re-assign their
 // angle, and to what (th2 is valid only where asg).  Returns the warp vote "some cell did data-dependent work".
-template <int JM, bool NOISE, bool ROT, bool GEN, class Draw>
+template <int PAR, int JM, bool NOISE, bool ROT, bool GEN, class Draw>
 __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const ColdK& K, float2 pn, float w, float ee, float2 tn,
                                          float tw, float te, const float (&th_old_in)[2], Draw&& draw, float2& np_, float2& nt_,
                                          float2& th2, bool (&asg)[2]) {
+    constexpr int OLD = PAR, NEW = PAR ^ 1;            // window slots: [OLD] = the older row (r-2 / r-3), [NEW] = the newer one
+    const float2 po0 = S.po[OLD], gx1 = S.gxw[NEW], gx2 = S.gxw[OLD], A2 = S.A[NEW], A3 = S.A[OLD], P3 = S.P[OLD];
     // horizontal neighbours of the pass-1 products of row r-2, issued early: the shuffle latency hides behind pass 1
-    const float A_w = __shfl_up_sync(0xffffffffu, S.A2.y, 1);
-    const float A_e = __shfl_down_sync(0xffffffffu, S.A2.x, 1);
+    const float A_w = __shfl_up_sync(0xffffffffu, A2.y, 1);
+    const float A_e = __shfl_down_sync(0xffffffffu, A2.x, 1);
     const float Q_w = __shfl_up_sync(0xffffffffu, S.Q2.y, 1);
     const float Q_e = __shfl_down_sync(0xffffffffu, S.Q2.x, 1);
     // ---- phi row r: horizontal sums and x-gradient; T row r-1: horizontal sums ----
@@ -312,12 +319,12 @@ __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const C
     const float2 gxn = f2mul(make_float2(pn.y - w, ee - pn.x), f2(C.idx));                    // :139
     const float2 thsum = make_float2(tw + tn.y, tn.x + te);
     // ---- pass 1 for row r-1, far-field values first ----
-    const float2 gyn = f2mul(f2sub(pn, S.po0), f2(C.idy));                                    // :140
-    float2 An = f2(C.A0), Pn = f2mul(f2(C.B0), S.gx1), Qn = f2mul(f2(C.B0), gyn);             // cells holding theta = 0
-    const float2 q = f2fma(f2neg(S.po0), S.po0, S.po0);                                       // phi (1 - phi) of row r-2
+    const float2 gyn = f2mul(f2sub(pn, po0), f2(C.idy));                                      // :140
+    float2 An = f2(C.A0), Pn = f2mul(f2(C.B0), gx1), Qn = f2mul(f2(C.B0), gyn);               // cells holding theta = 0
+    const float2 q = f2fma(f2neg(po0), po0, po0);                                             // phi (1 - phi) of row r-2
     float2 radd = f2(0.f);
-    asg[0] = (S.gx1.x < -K.e) || (fabsf(gyn.x) > K.e);                                        // :154-167: theta re-assigned
-    asg[1] = (S.gx1.y < -K.e) || (fabsf(gyn.y) > K.e);
+    asg[0] = (gx1.x < -K.e) || (fabsf(gyn.x) > K.e);                                          // :154-167: theta re-assigned
+    asg[1] = (gx1.y < -K.e) || (fabsf(gyn.y) > K.e);
     // Votes: `busy` = some cell re-assigns its angle or has phi (1 - phi) != 0 -> the whole data-dependent block; otherwise,
     // `held` = some cell carries a non-zero held angle (the inside of a saturated region: phi == 1 exactly, gradient in the
     // dead-band) -> only eps(theta) of those cells is evaluated; otherwise the far-field constants above stand.  A cell gets the
@@ -332,34 +339,34 @@ __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const C
         float2 rq = f2(0.f);
         if (NOISE) rq = draw();
         float2 Bn;
-        cold_block<JM, NOISE, ROT, GEN>(K, S.gx1, gyn, th_old, asg, S.po0, S.tq1, q, rq, An, Bn, th2, radd);
-        Pn = f2mul(Bn, S.gx1);
+        cold_block<JM, NOISE, ROT, GEN>(K, gx1, gyn, th_old, asg, po0, S.tq1, q, rq, An, Bn, th2, radd);
+        Pn = f2mul(Bn, gx1);
         Qn = f2mul(Bn, gyn);
     } else if (GEN) {
         const bool held = __any_sync(0xffffffffu, th_old_in[0] != 0.f || th_old_in[1] != 0.f);
         if (held) {
             float2 Bn;
             held_block<JM, ROT>(K, th_old_in, An, Bn);
-            Pn = f2mul(Bn, S.gx1);
+            Pn = f2mul(Bn, gx1);
             Qn = f2mul(Bn, gyn);
             vote = true;
         }
     }
     // ---- pass 2 for row r-2 ----
-    const float2 dA = make_float2(S.A2.y - A_w, A_e - S.A2.x);                                // :190-192
+    const float2 dA = make_float2(A2.y - A_w, A_e - A2.x);                                    // :190-192
     const float2 dQ = make_float2(Q_w - S.Q2.y, S.Q2.x - Q_e);                                // term2, :201-203
     const float2 gEx = f2mul(dA, f2(C.idx));
-    const float2 gEy = f2mul(f2sub(An, S.A3), f2(C.idy));                                     // :193-195
-    float2 sm = f2fma(f2sub(Pn, S.P3), f2(C.idy), radd);                                      // term1 (:197-199) + reaction
+    const float2 gEy = f2mul(f2sub(An, A3), f2(C.idy));                                       // :193-195
+    float2 sm = f2fma(f2sub(Pn, P3), f2(C.idy), radd);                                        // term1 (:197-199) + reaction
     sm = f2fma(dQ, f2(C.idx), sm);
-    sm = f2fma(S.A2, f2mul(S.lap2, f2(C.il)), sm);                                            // eps^2 * lap(phi)
-    sm = f2fma(gEx, S.gx2, sm);                                                               // term3, :204
+    sm = f2fma(A2, f2mul(S.lap2, f2(C.il)), sm);                                              // eps^2 * lap(phi)
+    sm = f2fma(gEx, gx2, sm);                                                                 // term3, :204
     sm = f2fma(gEy, S.gy2, sm);
-    np_ = f2fma(sm, f2(C.dtt), S.po0);                                                        // :211
+    np_ = f2fma(sm, f2(C.dtt), po0);                                                          // :211
     const float2 tu_new = f2fma(f2(2.0f), tn, thsum);                                         // u_T(r-1)
     const float2 lapt = f2add(S.tlp1, tu_new);                                                // 9-point sum of T at row r-2
-    nt_ = f2fma(f2(C.K), f2sub(np_, S.po0), f2fma(lapt, f2(C.ildt), S.tq1));                  // :215
-    // ---- rotate the windows ----
+    nt_ = f2fma(f2(C.K), f2sub(np_, po0), f2fma(lapt, f2(C.ildt), S.tq1));                    // :215
+    // ---- advance the windows: the [OLD] slots take this iteration's rows ----
     S.tlp1 = f2fma(f2(2.0f), thsum, f2fma(f2(-12.0f), tn, S.tu1));
     S.tu1 = tu_new;
     S.tq1 = tn;
@@ -367,10 +374,11 @@ __device__ __forceinline__ bool row_full(RowState& S, const RowConst& C, const C
     S.lap2 = f2add(S.lp1, u_new);
     S.lp1 = f2fma(f2(2.0f), hsum, f2fma(f2(-12.0f), pn, S.u1));
     S.u1 = u_new;
-    S.gx2 = S.gx1; S.gy2 = gyn; S.gx1 = gxn;
-    S.po0 = S.po1; S.po1 = pn;
-    S.A3 = S.A2; S.A2 = An;
-    S.P3 = S.P2; S.P2 = Pn;
+    S.gy2 = gyn;
+    S.gxw[OLD] = gxn;
+    S.po[OLD] = pn;
+    S.A[OLD] = An;
+    S.P[OLD] = Pn;
     S.Q2 = Qn;
     return vote;
 }

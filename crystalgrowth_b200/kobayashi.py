@@ -252,6 +252,8 @@ class Kobayashi:
         self.set_params(p)
         self.set_fields(phi, t, th)
         self.step_counter = h.step_counter
+        self._ck(self._L.kob_set_sim_counters(self._h, max(0, int(h.sim_frame)), self.simTime))   # _simFrame continues
+        # (a strip of a ring: follow with StripRing.refresh() / StripRing.load_checkpoint so that the neighbours see the rows)
 
     # ---- counters ----
     @property

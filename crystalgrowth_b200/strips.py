@@ -100,6 +100,15 @@ class StripRing:
             handles = exchange_blobs(self.strip.ipc_export(), rank, world,
                                      device=torch.device("cuda", device) if torch.cuda.is_available() else None)
             self.strip.ipc_link(handles[self.lower_rank], handles[self.upper_rank])
+            # ring-wide step-path agreement inside the library (kob_ring_join): rank 0 names the ring, everybody joins
+            self._lib_policy = False
+            if hasattr(self.strip, "ring_join") and getattr(self.strip, "kernel", "") == "fast":
+                import os
+                import time
+                token = (f"{os.getpid()}_{time.time_ns() & 0xffffffffff:x}".encode() + b"\0" * 48)[:48]
+                name = exchange_blobs(token, rank, world, device=torch.device("cuda", device) if torch.cuda.is_available() else None)[0]
+                self.strip.ring_join(name.rstrip(b"\0").decode(), rank, world)
+                self._lib_policy = True
             dist.barrier()
             self.refresh()
 
@@ -122,15 +131,17 @@ class StripRing:
             self.strip.add_nucleus(x, y)
         self.refresh()
 
-    # Linked strips must run the same launch sequence, so the library's own adaptive choice between the single-step kernel
-    # and two-step launch pairs is off inside a ring (pairs always).  The ring restores it: every POLICY_CHUNK sub-steps
-    # the strips' density probes are max-reduced and every rank switches the mode on the same sub-step.
+    # Linked strips must run the same launch sequence, so the library's per-context adaptive choice between the single-step
+    # kernel and two-step launch pairs is off inside a ring.  Strips that joined the ring in the library (kob_ring_join, the
+    # normal case) agree on the path by themselves; for strip objects without it the same policy is run here: every
+    # POLICY_CHUNK sub-steps the strips' density probes are max-reduced and every rank switches the mode on the same sub-step.
     POLICY_CHUNK = 64
     TO_SINGLE, TO_PAIRS = 0.04, 0.03
 
     def step(self, n: int = 1):
-        if self.world == 1 or not hasattr(self.strip, "set_path_mode") or getattr(self.strip, "kernel", "") != "fast":
-            self.strip.step(n)
+        if (self.world == 1 or getattr(self, "_lib_policy", False) or not hasattr(self.strip, "set_path_mode")
+                or getattr(self.strip, "kernel", "") != "fast"):
+            self.strip.step(n)                                      # the library agrees on the path across the ring by itself
             return
         import torch
         import torch.distributed as dist
@@ -154,3 +165,8 @@ class StripRing:
             self.strip.sync()
             dist.barrier()          # nobody unmaps memory a neighbour may still be storing into
         self.strip.close()
+
+    def load_checkpoint(self, path: str):
+        """Resume this rank's strip from its KOBCKPT1 file and bring the ring's ghost rows / theta flags up to date."""
+        self.strip.load_checkpoint(path)
+        self.refresh()

@@ -3,7 +3,7 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import crystalgrowth_b200 as cg  # noqa: E402
 from crystalgrowth_b200.strips import nuclei_positions  # noqa: E402
 

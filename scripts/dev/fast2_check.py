@@ -4,7 +4,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench  # noqa: E402
 import crystalgrowth_b200 as cg  # noqa: E402
 from crystalgrowth_b200.strips import partition  # noqa: E402
