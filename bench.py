@@ -13,8 +13,9 @@ One "step" = one call of the reference's plugin entry point Kobayashi::iUpdate (
 = `--substeps` (10) explicit-Euler sub-steps = 10 launches of the fused single-step kernel, or 5 two-step launch pairs
 (far pass + general pass; the library picks the path, results are bit-identical — kob_path_stats says which ran).
 
-  value  Gcell-updates/s with the state resident in HBM, CUDA-event timed on the library's stream, max over ranks; the timed
-         region (K steps) is run `--repeats` (3) times and the MEDIAN repeat is reported (all repeats under `repeats`)
+  value  Gcell-updates/s with the state resident in HBM, CUDA-event timed on the library's stream, max over ranks; the
+         measurement (fresh seeded field, W warm-up steps, K timed steps) is run `--repeats` (3) times and the MEDIAN repeat is
+         reported (all repeats under `repeats`; the crystals grow, so only identical step ranges are comparable)
   e2e    same metric through the host-buffer plugin call: every step copies phi, T, theta from pinned host
          memory to the device (kob_set_fields), runs the sub-steps, and reads phi and T back (kob_get_fields);
          `e2e_plugin` is the call shape of INTEGRATION.md §1 (state resident, kob_update + asynchronous phi readback)
@@ -344,10 +345,15 @@ def main():
     ring = StripRing(nx, nyg, 1e-4, rank=rank, world=world, device=local, precision=a.precision, kernel=a.kernel,
                      seed=SEED, noise_a=a.noise)
     sim = ring.strip
-    ring.seed_nuclei(nuclei_positions(a.nuclei * (16 if a.strong else world), nx, nyg, SEED))
-    if a.field == "dense":
-        sim.set_fields(*dense_state(nx, ring.ny, ring.y0), None)
-        ring.refresh()
+    nuclei = nuclei_positions(a.nuclei * (16 if a.strong else world), nx, nyg, SEED)
+
+    def fresh_field():
+        """The workload's initial state (every repeat starts from it: the crystals grow, so later steps cost more)."""
+        ring.seed_nuclei(nuclei)
+        if a.field == "dense":
+            sim.set_fields(*dense_state(nx, ring.ny, ring.y0), None)
+            ring.refresh()
+
     total_cells_per_step = nx * nyg * a.substeps
 
     def timed_region():
@@ -359,15 +365,20 @@ def main():
         wall = 1e3 * (time.perf_counter() - w0)
         return allmax([ms, wall])
 
-    # ---- warm-up, then the timed region `repeats` times (the field keeps evolving: repeat r covers steps r*K .. (r+1)*K) ----
-    for _ in range(max(a.warmup, 3)):
-        sim.step(a.substeps)
-    sim.sync()
+    # ---- `repeats` x (fresh seeded field, W warm-up steps, the timed region of K steps): every repeat times the SAME steps ----
     sampler = ClockSampler(local)
     sampler.start()
-    l0, p0 = sim.launch_count, sim.path_stats()
-    reps = [timed_region() for _ in range(max(1, a.repeats))]
-    launches, p1 = sim.launch_count - l0, sim.path_stats()
+    reps, launches, paired, single = [], 0, 0, 0
+    for _ in range(max(1, a.repeats)):
+        fresh_field()
+        for _ in range(max(a.warmup, 3)):
+            sim.step(a.substeps)
+        sim.sync()
+        l0, p0 = sim.launch_count, sim.path_stats()
+        reps.append(timed_region())
+        p1 = sim.path_stats()
+        launches = sim.launch_count - l0                      # kernels launched inside ONE timed region
+        paired, single = p1["paired_steps"] - p0["paired_steps"], p1["single_steps"] - p0["single_steps"]
     clocks = sampler.result()
     ms_list = [r[0] for r in reps]
     ms_med = median(ms_list)
@@ -377,8 +388,6 @@ def main():
     # The step path: single-step launches (one kernel per sub-step) and/or two-step launch pairs (far pass + general
     # pass = 2 kernels per 2 sub-steps).  A "launch" below is the unit that is timed: one sub-step for the single-step
     # kernel, one PAIR (two sub-steps) for the two-step path.
-    paired = p1["paired_steps"] - p0["paired_steps"]
-    single = p1["single_steps"] - p0["single_steps"]
     two_step = paired >= single
     sub_per_launch = 2 if two_step else 1
     launch_ms = ms_med / (a.steps * a.substeps) * sub_per_launch
@@ -389,7 +398,7 @@ def main():
             "traffic": None, "peak_source": peak_src,
             "kernel": ("kob_far2 + kob_step_fast2 (launch pair = 2 sub-steps)" if two_step else f"kob_step_{a.kernel}"),
             "algorithmic_bytes_per_cell_per_launch": 4 * elem, "substeps_per_launch": sub_per_launch, "launch_ms": launch_ms,
-            "paired_substeps": paired // max(1, a.repeats), "single_substeps": single // max(1, a.repeats),
+            "paired_substeps": paired, "single_substeps": single,
             "frac_sec8d_units": achieved * sub_per_launch / peak,
             "note": ("frac = bytes the launch must move (16 B per cell) / launch time / measured copy peak; a two-step launch pair "
                      "advances every cell by TWO sub-steps for those bytes, so in SURVEY §8d's units (16 B per cell-UPDATE) the "
@@ -414,8 +423,14 @@ def main():
 
     # ---- the SURVEY §8d kernel proper: one sub-step per launch on the same (seeded) workload ----
     if world == 1 and a.kernel == "fast" and a.field == "seeded" and not a.no_single and not a.strong:
+        s_all = []
         sim.set_path_mode(0)
-        s_ms, s_all = timed_leg(a.steps * a.substeps, 2 * a.substeps, max(1, a.repeats))
+        for _ in range(max(1, a.repeats)):                    # same protocol as the headline: fresh field, W warm-up steps, K timed steps
+            fresh_field()
+            sim.step(max(a.warmup, 3) * a.substeps)
+            sim.sync()
+            s_all.append(sim.step_timed(a.steps * a.substeps) / (a.steps * a.substeps))
+        s_ms = median(s_all)
         sim.set_path_mode(2)
         s_ach = cells * 4 * elem / (s_ms * 1e-3) / 1e9
         roof["single_step"] = {"kernel": "kob_step_fast", "launch_ms": s_ms, "value": cells / (s_ms * 1e-3) / 1e9, "unit": "Gcell/s",
@@ -457,19 +472,37 @@ def main():
         barrier()
         for it in range(a.e2e_steps + 1):
             if it == 1:                                   # first iteration is warm-up
+                sim.wait_fields()
                 barrier()
                 e0 = time.perf_counter()
+            sim.set_fields_from(bufs[0], bufs[1], bufs[2])    # H2D of this step's inputs (asynchronous, library stream)
+            if world > 1:
+                ring.refresh()
+            sim.step(a.substeps)
+            # D2H of this step's result: snapshot on the device, copy on the library's second stream — it overlaps the NEXT
+            # step's H2D (PCIe is full duplex); kob_wait_fields before the clock stops
+            sim.get_fields_async(bufs[3], bufs[4], None)
+        sim.wait_fields()
+        barrier()
+        e_ms = allmax([1e3 * (time.perf_counter() - e0)])[0]
+        e2e = {"value": total_cells_per_step * a.e2e_steps / (e_ms * 1e-3) / 1e9, "unit": "Gcell/s",
+               "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": 2 * nbytes * world,
+               "steps": a.e2e_steps, "ms_per_step": e_ms / a.e2e_steps,
+               "call": "per step: kob_set_fields(phi,T,theta) + kob_step(substeps) + kob_get_fields_async(phi,T); kob_wait_fields at the "
+                       "end; pinned NUMA-local host buffers (step n's readback overlaps step n+1's upload)"}
+        # the round-1 call shape for comparison on the same box: blocking readback, nothing overlaps
+        barrier()
+        s0_ = time.perf_counter()
+        for it in range(a.e2e_steps):
             sim.set_fields_from(bufs[0], bufs[1], bufs[2])
             if world > 1:
                 ring.refresh()
             sim.step(a.substeps)
             sim.get_fields_into(bufs[3], bufs[4], None)
         barrier()
-        e_ms = allmax([1e3 * (time.perf_counter() - e0)])[0]
-        e2e = {"value": total_cells_per_step * a.e2e_steps / (e_ms * 1e-3) / 1e9, "unit": "Gcell/s",
-               "h2d_bytes_per_step": 3 * nbytes * world, "d2h_bytes_per_step": 2 * nbytes * world,
-               "steps": a.e2e_steps, "ms_per_step": e_ms / a.e2e_steps,
-               "call": "kob_set_fields(phi,T,theta) + kob_step(substeps) + kob_get_fields(phi,T), pinned NUMA-local host buffers"}
+        sm_ = allmax([1e3 * (time.perf_counter() - s0_)])[0]
+        e2e["serial_value"] = total_cells_per_step * a.e2e_steps / (sm_ * 1e-3) / 1e9
+        e2e["serial_call"] = "kob_set_fields + kob_step + blocking kob_get_fields (the round-1 measurement)"
         # the plugin's own call shape: state resident, iUpdate, then the picture's phi read back —
         # asynchronously, double buffered, so that frame n's copy overlaps frame n+1's sub-steps
         barrier()

@@ -429,10 +429,10 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         if (c->worklist_cap < njobs) {
             if (c->worklist) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->worklist); c->worklist = nullptr; }
             KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(F2_RANGES * njobs + 4) * sizeof(int)));
+            KOB_CUDA(c, cudaMemsetAsync(c->worklist, 0, 4 * sizeof(int), c->stream));   // header: armed once; each general pass re-arms it
             c->worklist_cap = njobs;
         }
-        unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim
-        KOB_CUDA(c, cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), c->stream));
+        unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim, [2] exits, [3] last count
         const int far_smem = FAR2_WARPS * FAR2_WARP_BYTES + FAR2_WARPS * FAR2_NST * 8;
         int fcps = 0;
         KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kob_far2), FAR2_WARPS * 32, far_smem, &fcps));
@@ -448,7 +448,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;
         kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
         if (!c->count_pending && c->h_count) {                            // density probe (adaptive policy / kob_path_stats)
-            KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+            KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
             KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
             c->count_pending = true;
         c->probe_launch = c->launches;

@@ -95,7 +95,7 @@ __device__ __forceinline__ void f2_row(RowState& S, const FastArgs& f, float2 pn
 //   2. kob_step_fast2 then processes the work list.
 struct Far2Args {
     int* list;                  // job ids for the general pass
-    unsigned int* list_count;   // entries appended by this launch (zeroed by the host before it)
+    unsigned int* list_count;   // entries appended by this launch (re-armed to 0 by the previous general pass)
 };
 
 constexpr int FAR2_WARPS = 8;
@@ -331,7 +331,19 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
             unsigned int idx = 0;
             if (lane == 0) idx = atomicAdd(f.list_claim, 1u);
             idx = __shfl_sync(0xffffffffu, idx, 0);
-            if (idx >= *f.list_count) break;
+            if (idx >= *f.list_count) {
+                // the list is drained for this warp.  The LAST warp of the grid to get here re-arms the header for the next launch
+                // pair (count, claim, exits = 0; the count is kept in word 3 for the host's density probe): no memset per pair.
+                if (lane == 0) {
+                    unsigned int* hdr = f.list_claim - 1;                    // [count, claim, exits, last count]
+                    if (atomicAdd(&hdr[2], 1u) + 1u == gridDim.x * (blockDim.x >> 5)) {
+                        hdr[3] = hdr[0];
+                        hdr[0] = 0u; hdr[1] = 0u; hdr[2] = 0u;
+                        __threadfence();
+                    }
+                }
+                break;
+            }
             jraw = (unsigned long long)f.list[idx];
             sub = (int)(jraw & (unsigned long long)(F2_RANGES - 1));   // the far pass cuts a job into F2_RANGES row ranges:
             jraw /= F2_RANGES;                               // short jobs keep the (latency-bound) general pass short

@@ -470,6 +470,83 @@ def test_errors_are_reported_not_thrown(po, cg):
         g.set_fields(np.zeros((3, 3), np.float32))
 
 
+def test_window_access_and_async_readback(po, cg):
+    """kob_get_window / kob_set_window (sub-rectangles; periodic aliases of written seam cells refreshed), kob_get_fields_async +
+    kob_wait_fields (snapshot, then stepping continues while the copy runs), kob_host_alloc_near (pinned, NUMA-near)."""
+    import ctypes as C
+    for kernel in ("fast", "strict"):
+        nx, ny = 300, 200
+        g = cg.Kobayashi(nx, ny, 1e-4, kernel=kernel, noise_a=0.01, seed=4)
+        g.step(30)
+        phi, t, th = g.fields()
+        for (x0, y0, w, h) in [(0, 0, 7, 5), (120, 80, 64, 40), (nx - 9, ny - 6, 9, 6), (0, 0, nx, ny)]:
+            a, b, c_ = g.window(x0, y0, w, h)
+            assert bit_equal(a, phi[y0:y0 + h, x0:x0 + w]) and bit_equal(b, t[y0:y0 + h, x0:x0 + w]) and bit_equal(c_, th[y0:y0 + h, x0:x0 + w])
+        with pytest.raises(cg.KobayashiError):
+            g.window(nx - 3, 0, 8, 4)
+        # a window written over the x seam and the y seam must step like the same state written whole
+        rng = np.random.default_rng(3)
+        patch = (0.5 + 0.4 * rng.random((6, 9))).astype(np.float32)
+        g2 = cg.Kobayashi(nx, ny, 1e-4, kernel=kernel, noise_a=0.01, seed=4)
+        g2.set_fields(phi, t, th)
+        g2.step_counter = g.step_counter
+        phi2 = phi.copy()
+        phi2[ny - 6:, nx - 9:] = patch
+        g.set_window(nx - 9, ny - 6, phi=patch)
+        g2.set_fields(phi2, t, th)
+        g.step(3)
+        g2.step(3)
+        assert all(bit_equal(x, y) for x, y in zip(g.fields(), g2.fields()))
+        # asynchronous readback: the snapshot is the state at the call, whatever is queued afterwards
+        n = nx * ny * 4
+        bufs = [g.host_alloc_near(n) for _ in range(3)]
+        want = g.fields()
+        g.get_fields_async(bufs[0], bufs[1], bufs[2])
+        g.step(5)
+        g.wait_fields()
+        for k in range(3):
+            got = np.frombuffer((C.c_char * n).from_address(bufs[k].value), np.float32).reshape(ny, nx)
+            assert bit_equal(got.copy(), want[k])
+        L = cg.load()
+        for p_ in bufs:
+            assert L.kob_host_free(p_) == 0
+        g.close()
+        g2.close()
+
+
+def test_ring_guards(cg):
+    """Linked strips must run one launch sequence: thin FAST strips are refused, a host-injected noise field needs the
+    ring in single-step mode, kob_ring_join checks its arguments."""
+    a = cg.Kobayashi(64, 6, 1e-4, kernel="fast", ny_global=38, y0=0)
+    b = cg.Kobayashi(64, 32, 1e-4, kernel="fast", ny_global=38, y0=6)
+    with pytest.raises(cg.KobayashiError) as e:
+        a.link_local(b, b)
+    assert "8 rows" in str(e.value)
+    s0 = cg.Kobayashi(64, 32, 1e-4, kernel="fast", ny_global=64, y0=0, noise_a=0.01)
+    s1 = cg.Kobayashi(64, 32, 1e-4, kernel="fast", ny_global=64, y0=32, noise_a=0.01)
+    s0.link_local(s1, s1)
+    s1.link_local(s0, s0)
+    r = np.full((32, 64), 0.25, np.float32)
+    with pytest.raises(cg.KobayashiError):
+        s0.set_noise_field(r)
+    for s in (s0, s1):
+        s.set_path_mode(0)
+    s0.set_noise_field(r)
+    s1.set_noise_field(r)
+    for s in (s0, s1):
+        s.halo_refresh()
+    for s in (s0, s1):
+        s.step(4)
+    for s in (s0, s1):
+        s.sync()
+    with pytest.raises(cg.KobayashiError):
+        s0.ring_join("x" * 60, 0, 2)
+    with pytest.raises(cg.KobayashiError):
+        s0.ring_join("ok", 2, 2)
+    for s in (a, b, s0, s1):
+        s.close()
+
+
 def test_render_matches_reference_colours(po, cg):
     """kob_render_rgba vs the colours the REFERENCE gives every object (iUpdateConstantBuffer, src/Kobayashi.cpp:309-345):
     the committed fixture tests/golden/ref_colors_n48.npz was produced by the reference TU (scripts/make_golden.py,
