@@ -379,6 +379,8 @@ def main():
         p1 = sim.path_stats()
         launches = sim.launch_count - l0                      # kernels launched inside ONE timed region
         paired, single = p1["paired_steps"] - p0["paired_steps"], p1["single_steps"] - p0["single_steps"]
+        conc_pairs = p1["concurrent_pairs"] - p0["concurrent_pairs"]
+        listed_frac = p1["dense_fraction"]
     clocks = sampler.result()
     ms_list = [r[0] for r in reps]
     ms_med = median(ms_list)
@@ -399,6 +401,7 @@ def main():
             "kernel": ("kob_far2 + kob_step_fast2 (launch pair = 2 sub-steps)" if two_step else f"kob_step_{a.kernel}"),
             "algorithmic_bytes_per_cell_per_launch": 4 * elem, "substeps_per_launch": sub_per_launch, "launch_ms": launch_ms,
             "paired_substeps": paired, "single_substeps": single,
+            "pairs_with_concurrent_general_pass": conc_pairs, "listed_range_fraction_last_probe": listed_frac,
             "frac_sec8d_units": achieved * sub_per_launch / peak,
             "note": ("frac = bytes the launch must move (16 B per cell) / launch time / measured copy peak; a two-step launch pair "
                      "advances every cell by TWO sub-steps for those bytes, so in SURVEY §8d's units (16 B per cell-UPDATE) the "

@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <thread>
 
@@ -19,6 +20,7 @@
 #include <new>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/kobayashi_c.h"
 #include "kob_aux.cuh"
@@ -142,19 +144,67 @@ struct kob_ctx {
     uint64_t ring_steps = 0, ring_round = 0;
     std::string ring_name;
     int fast2_yj = 96, fast2_yj_b = 32, fast2_lock = 0, fast2_far = 1, fast2_far_cta = 1;
-    int* worklist = nullptr;      // far/general launch pair: [count, claim, -, -, job ids ...]
+    int* worklist = nullptr;      // far/general launch pair: 8 header words (FastArgs::list), then the row-range ids (-1 = empty slot)
     long long worklist_cap = 0;
+    unsigned char* hot = nullptr; // [2][units]: claim units of the far pass that listed something in the previous / this pair
+    long long hot_units = 0;
+    int hot_par = 0;
+    // The general pass beside the far pass (programmatic dependent launch) while the work list is short: KOB_FAST2_CONC = 0 never,
+    // otherwise the largest list (row ranges) it is used for.
+    int fast2_conc = 1 << 30;
+    double fast2_ticket_us = 85.0; // what a listed row range costs a warp of the general pass
+    int fast2_conc_sm = 24;       // the most SMs the general pass may take from the far pass
+    long long list_est = -1;      // length of the last probed work list (-1: none yet)
+    bool probe_is_list = false;
+    uint64_t n_conc = 0;
+    bool registered = false;      // counted in g_ctx_on_device
     unsigned long long job_expected = 0;   // value of the device job counter before the next launch
     int64_t frames = 0;
     double sim_ms = 0.0;
     std::string err;
+    // KOB_TRACE=<file>: CUDA events around the step kernels' launches (first 4096), written as CSV at kob_destroy
+    std::string trace_path;
+    std::vector<cudaEvent_t> trace_ev;
+    std::vector<const char*> trace_name;
 };
 
 namespace {
 
+// contexts of this process per device: the concurrent general pass needs SMs of its own, which only a context that has the
+// device to itself can count on
+std::atomic<int> g_ctx_on_device[64];
+
 int fail(kob_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
+}
+
+// Launch trace (diagnostics): event before / after a kernel launch on the context's stream.
+inline void trace_mark(kob_ctx* c, const char* name) {
+    if (c->trace_path.empty() || c->trace_ev.size() >= 8192) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c->stream);
+    c->trace_ev.push_back(e);
+    c->trace_name.push_back(name);
+}
+void trace_dump(kob_ctx* c) {
+    if (c->trace_path.empty() || c->trace_ev.size() < 2) return;
+    cudaStreamSynchronize(c->stream);
+    if (FILE* fh = std::fopen(c->trace_path.c_str(), "w")) {
+        std::fprintf(fh, "kernel,start_us,duration_us,gap_before_us\n");
+        float prev_end = 0.f;
+        for (size_t i = 0; i + 1 < c->trace_ev.size(); i += 2) {
+            float t0 = 0.f, dt = 0.f;
+            cudaEventElapsedTime(&t0, c->trace_ev[0], c->trace_ev[i]);
+            cudaEventElapsedTime(&dt, c->trace_ev[i], c->trace_ev[i + 1]);
+            std::fprintf(fh, "%s,%.2f,%.2f,%.2f\n", c->trace_name[i], t0 * 1e3f, dt * 1e3f, (t0 - prev_end) * 1e3f);
+            prev_end = t0 + dt;
+        }
+        std::fclose(fh);
+    }
+    for (cudaEvent_t e : c->trace_ev) cudaEventDestroy(e);
+    c->trace_ev.clear(); c->trace_name.clear();
 }
 
 #define KOB_CUDA(c, call)                                                                         \
@@ -334,11 +384,14 @@ int launch_fast_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         KOB_CUDA(c, cudaMemsetAsync(live_ctr, 0, sizeof(unsigned int), c->stream));
         f.live_ctr = live_ctr;
     }
+    trace_mark(c, "kob_step_fast");
     kern<<<grid, FAST_WARPS * 32, smem, c->stream>>>(c->maps_io, a, f);
+    trace_mark(c, "");
     if (probe) {
         KOB_CUDA(c, cudaMemcpyAsync(c->h_count, live_ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
         KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
         c->count_pending = true;
+        c->probe_is_list = false;
         c->probe_launch = c->launches;
         c->count_total = (long long)f.nstrips * f.nseg;
     }
@@ -426,32 +479,82 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
     const long long njobs = (long long)(f.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
     if (c->fast2_far && !f.cta_jobs) {
         // far/general launch pair: the light far pass visits every job and leaves the rest on the work list
+        constexpr int HDR = LH_WORDS;
         if (c->worklist_cap < njobs) {
             if (c->worklist) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->worklist); c->worklist = nullptr; }
-            KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(F2_RANGES * njobs + 4) * sizeof(int)));
-            KOB_CUDA(c, cudaMemsetAsync(c->worklist, 0, 4 * sizeof(int), c->stream));   // header: armed once; each general pass re-arms it
+            KOB_CUDA(c, cudaMalloc((void**)&c->worklist, (size_t)(F2_RANGES * njobs + HDR) * sizeof(int)));
+            KOB_CUDA(c, cudaMemsetAsync(c->worklist, 0, HDR * sizeof(int), c->stream));   // header: armed once; each pair's last launch re-arms it
+            KOB_CUDA(c, cudaMemsetAsync(c->worklist + LH_MIN, 0xff, sizeof(int), c->stream));
+            KOB_CUDA(c, cudaMemsetAsync(c->worklist + HDR, 0xff, (size_t)F2_RANGES * njobs * sizeof(int), c->stream));   // all slots empty
             c->worklist_cap = njobs;
         }
-        unsigned int* counters = reinterpret_cast<unsigned int*>(c->worklist);          // [0] count, [1] claim, [2] exits, [3] last count
+        unsigned int* hdr = reinterpret_cast<unsigned int*>(c->worklist);
         const int far_smem = FAR2_WARPS * FAR2_WARP_BYTES + FAR2_WARPS * FAR2_NST * 8;
         int fcps = 0;
         KOB_TRY(kernel_occupancy(c, reinterpret_cast<const void*>(kob_far2), FAR2_WARPS * 32, far_smem, &fcps));
-        Far2Args w{c->worklist + 4, counters};
         FastArgs ff = f;
         ff.cta_jobs = f.nstrips < FAR2_WARPS ? 0 : c->fast2_far_cta;      // narrow grids: a CTA job would be mostly padding
         const long long fjobs = (long long)(ff.cta_jobs ? f.nstrips_p : f.nstrips) * f.nseg;
+        const long long units = ff.cta_jobs ? fjobs / FAR2_WARPS : fjobs;
+        if (c->hot_units != units) {
+            if (c->hot) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->hot); c->hot = nullptr; }
+            KOB_CUDA(c, cudaMalloc((void**)&c->hot, (size_t)(2 * units)));
+            KOB_CUDA(c, cudaMemsetAsync(c->hot, 0, (size_t)(2 * units), c->stream));
+            c->hot_units = units;
+        }
+        Far2Args w{c->worklist + HDR, hdr, c->hot + (size_t)c->hot_par * units, c->hot + (size_t)(c->hot_par ^ 1) * units, 1};
+        c->hot_par ^= 1;
         ff.job_base = c->job_expected;
-        const int fgrid = (int)std::min<long long>((long long)nsm * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
-        kob_far2<<<fgrid, FAR2_WARPS * 32, far_smem, c->stream>>>(c->maps_far, a, ff, w);
+        f.list = c->worklist + HDR; f.list_count = hdr + LH_COUNT; f.list_claim = hdr + LH_CLAIM;
+        f.list_cap = (unsigned int)(F2_RANGES * njobs);
+        // Short list (the last probe says so): the general pass goes FIRST, on a few SMs of its own, and serves the list while the far
+        // pass — a programmatic dependent launch, started as soon as the general pass is resident — streams the grid.  A 1-CTA launch
+        // of the general pass closes the pair (normally it finds nothing; if the kernels were serialised it does the work).
+        // How many SMs: a ticket (one row range) takes a warp ~85 us; the far pass streams ~2.75 ps per cell and hardly slows down
+        // while it loses up to ~1/6 of the SMs (measured at 16384^2: 24 of 148 cost it 4 %, 37 cost 13 %).  The general pass must be
+        // able to serve the whole list during the far pass — serving part of it buys nothing, the rest would still cost the closing
+        // launch one ticket time (measured) — so longer lists keep the plain far -> general order.
+        const double far_us = 2.75e-6 * (double)c->nx * (double)c->ny;
+        const long long per_warp = std::max<long long>(1, (long long)(0.9 * far_us / c->fast2_ticket_us));
+        const long long need_sm = (std::max<long long>(c->list_est, 0) + 8 * per_warp - 1) / (8 * per_warp) + 1;
+        const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm / 4));
+        const bool conc = c->fast2_conc > 0 && c->list_est >= 0 && c->list_est <= c->fast2_conc && c->device < 64 &&
+                          g_ctx_on_device[c->device].load() == 1 && nsm >= 16 && 4 * need_sm <= 5 * cap_sm;
+        const int gsm = conc ? (int)std::min<long long>(need_sm, cap_sm) : 0;
+        const bool drain = true;
+        const int fgrid = (int)std::min<long long>((long long)(nsm - gsm) * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
+        trace_mark(c, conc ? "pair(general || far2)" : "kob_far2");
+        if (conc) {
+            f.list_conc = 1; f.list_rearm = 0; f.list_drain = drain ? 1 : 0;
+            kern<<<gsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)fgrid); cfg.blockDim = dim3(FAR2_WARPS * 32); cfg.dynamicSmemBytes = (size_t)far_smem; cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            KOB_CUDA(c, cudaLaunchKernelEx(&cfg, kob_far2, c->maps_far, a, ff, w));
+            f.list_conc = 0; f.list_rearm = 1; f.list_drain = 1;
+            kern<<<drain ? 1 : nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+            trace_mark(c, "");
+            c->n_conc += 1;
+        } else {
+            kob_far2<<<fgrid, FAR2_WARPS * 32, far_smem, c->stream>>>(c->maps_far, a, ff, w);
+            trace_mark(c, "");
+            f.list_conc = 0; f.list_rearm = 1; f.list_drain = 1;
+            trace_mark(c, "kob_step_fast2(list)");
+            kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+            trace_mark(c, "");
+        }
+        // every far-pass warp / CTA overshoots the job counter once
         c->job_expected += (unsigned long long)fjobs + (unsigned long long)fgrid * FAR2_WARPS;
-        c->launches += 1;
-        f.list = c->worklist + 4; f.list_count = counters; f.list_claim = counters + 1;
-        kern<<<nsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+        c->launches += conc ? 2 : 1;
         if (!c->count_pending && c->h_count) {                            // density probe (adaptive policy / kob_path_stats)
-            KOB_CUDA(c, cudaMemcpyAsync(c->h_count, counters + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+            KOB_CUDA(c, cudaMemcpyAsync(c->h_count, hdr + LH_LAST, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
             KOB_CUDA(c, cudaEventRecord(c->ev_count, c->stream));
             c->count_pending = true;
-        c->probe_launch = c->launches;
+            c->probe_is_list = true;
+            c->probe_launch = c->launches;
             c->count_total = (long long)F2_RANGES * f.nstrips * f.nseg;
         }
         return KOB_OK;
@@ -553,6 +656,7 @@ int rebuild_flags_impl(kob_ctx* c) {
     dim3 grid(c->L.nfbx, c->L.nfby);
     kob_rebuild_flags<real><<<grid, 256, 0, c->stream>>>(a.self.theta, a.self.tflags, c->L.pitch, c->L.rows, c->L.nfbx);
     KOB_CUDA(c, cudaGetLastError());
+    c->list_est = -1;             // the host wrote fields: what the last probe said about the work list no longer holds
     c->launches += 1;
     return KOB_OK;
 }
@@ -650,6 +754,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
     c->params = p;
     c->L = make_layout(nx, ny, c->prec);
     auto bail = [&](int code, const std::string& m) { g_create_error = m; kob_destroy(c); return code; };
+    if (c->device < 64) { g_ctx_on_device[c->device].fetch_add(1); c->registered = true; }
     cudaError_t e;
     if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
     if ((e = cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, c->device)) != cudaSuccess) return bail(KOB_ERR_CUDA, cudaGetErrorString(e));
@@ -674,6 +779,10 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2")) { c->fast2 = std::min(2, std::max(0, std::atoi(e_))); c->single_mode = c->fast2 == 0; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) { c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_)); c->fast2_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_TRACE")) c->trace_path = e_;
+        if (const char* e_ = std::getenv("KOB_FAST2_CONC")) c->fast2_conc = std::max(0, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_TICKET_US")) c->fast2_ticket_us = std::max(1.0, std::atof(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_CONC_SM")) c->fast2_conc_sm = std::max(1, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_LOCK")) c->fast2_lock = std::min(2, std::max(0, std::atoi(e_)));   // 0 per-warp jobs, 1 CTA jobs, 2 CTA jobs in lock-step
@@ -693,6 +802,8 @@ int kob_destroy(kob_ctx* c) {
     if (!c) return KOB_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->registered) g_ctx_on_device[c->device].fetch_sub(1);
+    trace_dump(c);
     if (c->lower.ipc && c->lower.base) cudaIpcCloseMemHandle(c->lower.base);
     if (c->upper.ipc && c->upper.base && c->upper.base != c->lower.base) cudaIpcCloseMemHandle(c->upper.base);
     if (c->ring) {
@@ -706,6 +817,7 @@ int kob_destroy(kob_ctx* c) {
     if (c->noise_field) cudaFree(c->noise_field);
     if (c->rgba) cudaFree(c->rgba);
     if (c->worklist) cudaFree(c->worklist);
+    if (c->hot) cudaFree(c->hot);
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->ev_count) cudaEventDestroy(c->ev_count);
     if (c->base) cudaFree(c->base);
@@ -759,6 +871,7 @@ void poll_density_probe(kob_ctx* c) {
     if (!c->count_pending || cudaEventQuery(c->ev_count) != cudaSuccess) return;
     c->count_pending = false;
     c->general_frac = (double)c->h_count[0] / (double)c->count_total;
+    c->list_est = c->probe_is_list ? (long long)c->h_count[0] : -1;       // a short list lets the general pass run beside the far pass
     if (c->fast2 == 2 && !c->linked) {
         if (!c->single_mode && c->general_frac > FAST2_TO_SINGLE) c->single_mode = true;
         else if (c->single_mode && c->general_frac < FAST2_TO_PAIR) c->single_mode = false;
@@ -849,13 +962,14 @@ int kob_update(kob_ctx* c) {
 // Linked strips: did an edge tile give up waiting for a neighbour, or see it run another launch sequence (kob_common.cuh, wait_flag)?
 static int fault_status(kob_ctx* c, uint32_t fault) {
     if (fault == 0) return KOB_OK;
+    if (fault == 3) return fail(c, KOB_ERR_STATE, "the general pass of a launch pair waited 20 s beside its far pass; fields are invalid");
     return fail(c, KOB_ERR_STATE, fault == 2 ? "a neighbour strip runs a different launch sequence (single steps vs two-step pairs): "
                                                "set the same path mode on every strip of the ring; fields are invalid"
                                              : "a neighbour strip did not reach the expected step within 20 s "
                                                "(strips must be stepped together); fields are invalid");
 }
 static int check_fault(kob_ctx* c) {
-    if (!c->linked) return KOB_OK;
+    if (!c->linked && c->n_conc == 0) return KOB_OK;
     uint32_t fault = 0;
     KOB_CUDA(c, cudaMemcpyAsync(&fault, c->base + c->L.off_arrive + 8, 4, cudaMemcpyDeviceToHost, c->stream));
     KOB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -863,7 +977,7 @@ static int check_fault(kob_ctx* c) {
 }
 // After the copy stream has drained: look at the fault word without touching the compute stream's queue.
 static int check_fault_nosync(kob_ctx* c) {
-    if (!c->linked) return KOB_OK;
+    if (!c->linked && c->n_conc == 0) return KOB_OK;
     uint32_t fault = 0;
     KOB_CUDA(c, cudaMemcpyAsync(&fault, c->base + c->L.off_arrive + 8, 4, cudaMemcpyDeviceToHost, c->copy_stream));
     KOB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
@@ -1036,6 +1150,7 @@ int kob_path_stats(const kob_ctx* c, uint64_t* single_steps, uint64_t* paired_st
     if (single_mode) *single_mode = c->single_mode ? 1 : 0;
     return KOB_OK;
 }
+int kob_concurrent_pairs(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->n_conc; return KOB_OK; }
 int kob_launch_count(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->launches; return KOB_OK; }
 int kob_get_dims(const kob_ctx* c, int64_t* nx, int64_t* ny, int64_t* nyg, int64_t* y0) {
     if (!c) return KOB_ERR_INVALID_ARG;

@@ -59,9 +59,15 @@ struct FastArgs {
     uint32_t pc2, pc3;             // Philox counter words 2, 3 = (step_lo, step_hi)
     long long ny_global;           // rows of the whole torus (two-step kernel: noise of wrapped ghost rows)
     // two-step kernel, general pass: jobs come from the work list the far pass wrote (nullptr: all jobs, from job_ctr)
-    const int* list;
+    // (header words before the list, LH_*: see kob_fast2.cuh)
+    int* list;
     const unsigned int* list_count;
     unsigned int* list_claim;
+    unsigned int list_cap;         // entries the list can hold
+    int list_conc;                 // this general pass was launched BEFORE its far pass and runs beside it (tickets are waited for)
+    int list_drain;                // ... and stays until every listed range is served (0: leaves when the far pass is done; the
+                                   // closing launch, a full grid then, serves the rest)
+    int list_rearm;                // this launch is the last of the pair: its last warp re-arms the header
     unsigned int* live_ctr;        // single-step kernel, probe launches only: counts the jobs that see live theta flags
     // linked strips: seam readiness is published per side as soon as the jobs touching that seam are done
     unsigned int* seam_ctr;        // [2]: low-side / high-side jobs completed in this launch (reset by the publisher)
@@ -156,6 +162,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
+
+// The same with pre-computed 32-bit shared addresses (callers make them warp-uniform with a shuffle first: ptxas then moves each
+// operand to a uniform register once, instead of wrapping every UTMALDG in an ELECT / R2UR.BROADCAST loop).
+__device__ __forceinline__ void tma_load_2d_raw(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 // ---- rare paths, kept out of line so that the steady-state row loop stays small in the instruction cache ----
 // Store to every alias of an owned seam cell (own ghost columns, neighbour strips' ghost rows).
@@ -386,19 +402,23 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
             constexpr int OUT0 = GEN ? FAST_R1_OUT : FAST_R0_OUT, OBUF = GEN ? FAST_R1_OBUF : FAST_R0_OBUF;
             uint64_t* bars = GEN ? bars1 : bars0;
             unsigned int& gchunk = GEN ? gch1 : gch0;
-            auto issue = [&](int c) {                    // lane 0: chunk c of this job -> stage ((gchunk + c) % NST)
-                const unsigned int gi = gchunk + (unsigned int)c;
+            const int box_xu = warp_uniform(box_x), ybase = warp_uniform(y0 - 2 + GY);
+            const unsigned int gchunk_u = (unsigned int)warp_uniform((int)gchunk);
+            const uint32_t region32 = (uint32_t)warp_uniform((int)smem_u32(region)), bars32 = (uint32_t)warp_uniform((int)smem_u32(bars));
+            auto issue = [&](int c) {                    // chunk c of this job -> stage ((gchunk + c) % NST); called by the whole warp
+                const int cu = warp_uniform(c);
+                const unsigned int gi = gchunk_u + (unsigned int)cu;
                 const int st = gi % NST;
-                unsigned char* dst = region + st * STAGE;
-                mbar_expect_tx(&bars[st], (GEN ? 3 : 2) * RB * BW * 4);
-                const int yr = y0 - 2 + c * RB + GY;     // padded row of the chunk's first phi row
-                tma_load_2d(dst, map_phi, box_x, yr, &bars[st]);
-                tma_load_2d(dst + FAST_BOX_BYTES, map_t, box_x, yr - 1, &bars[st]);
-                if (GEN) tma_load_2d(dst + 2 * FAST_BOX_BYTES, map_th, box_x, yr - 1, &bars[st]);     // theta rows = the T rows
+                const uint32_t dst = region32 + st * STAGE, bar = bars32 + st * 8;
+                const int yr = ybase + cu * RB;          // padded row of the chunk's first phi row
+                if (lane == 0) {
+                    mbar_expect_tx(&bars[st], (GEN ? 3 : 2) * RB * BW * 4);
+                    tma_load_2d_raw(dst, map_phi, box_xu, yr, bar);
+                    tma_load_2d_raw(dst + FAST_BOX_BYTES, map_t, box_xu, yr - 1, bar);
+                    if (GEN) tma_load_2d_raw(dst + 2 * FAST_BOX_BYTES, map_th, box_xu, yr - 1, bar);   // theta rows = the T rows
+                }
             };
-            if (lane == 0) {
-                for (int c = 0; c < NST && c < nch; ++c) issue(c);
-            }
+            for (int c = 0; c < NST && c < nch; ++c) issue(c);
             RowState S;
             S.clear();
             bool prevz = false;                          // !GEN: the previous chunk's phi rows were all +0
@@ -529,8 +549,8 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                         tma_store_2d(omap_th, ox, oy, obuf + 2 * FAST_OBOX_BYTES);
                         tma_store_commit();
                     }
-                    if (c + NST < nch) issue(c + NST);
                 }
+                if (c + NST < nch) issue(c + NST);
                 if (GEN) __syncwarp();
             }
             gchunk += (unsigned int)nch;

@@ -93,10 +93,37 @@ __device__ __forceinline__ void f2_row(RowState& S, const FastArgs& f, float2 pn
 //      into F2_RANGES row ranges; ranges with unstored rows are appended to the work list (rows both passes store get the same
 //      bits twice).
 //   2. kob_step_fast2 then processes the work list.
-struct Far2Args {
-    int* list;                  // job ids for the general pass
-    unsigned int* list_count;   // entries appended by this launch (re-armed to 0 by the previous general pass)
+//   Hot units first: a claim unit (a CTA job of 8 strips, or a job) that listed something in the previous pair is visited before
+//   all others (`hot_prev`, one byte per unit, written as `hot_next` by the previous far pass), so that the general pass — launched
+//   BEFORE this kernel on a few SMs of its own and running beside it (programmatic dependent launch) — gets its work list within the
+//   first microseconds and is done long before the far pass has streamed the rest of the grid.
+// Work-list header (unsigned words in front of the list; all zero = armed, except LH_MIN = ~0):
+enum : int {
+    LH_COUNT = 0,     // entries appended by the far pass of this pair
+    LH_CLAIM = 1,     // next ticket of the general pass
+    LH_GEXITS = 2,    // warps of the running general-pass launch that have left
+    LH_FEXITS = 4,    // far-pass warps that have left
+    LH_FDONE = 5,     // 1: the far pass is complete, LH_COUNT is final
+    LH_HOTCLAIM = 6,  // far pass, hot units first: next chunk of 64 units
+    LH_STATE = 7,     // 0 / 1 = a general pass launched before its far pass gave up waiting for it / 2 = the far pass has started
+    LH_MIN = 8,       // smallest ticket a general-pass warp left with unserved
+    LH_LAST = 12,     // count of the previous pair (host density probe)
+    LH_WORDS = 16
 };
+struct Far2Args {
+    int* list;                  // job ids for the general pass (-1 = empty slot)
+    unsigned int* hdr;          // work-list header
+    const unsigned char* hot_prev;
+    unsigned char* hot_next;
+    int hot_first;
+};
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int FAR2_WARPS = 8;
 constexpr int FAR2_NST = 4;
@@ -126,20 +153,60 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
     const long long pitch = a.pitch;
     unsigned int gchunk = 0;
     __shared__ unsigned long long s_job;
+    __shared__ int s_hot;
     const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
     const int njobs_q = nsp * f.nseg;
+    const unsigned int nunits = f.cta_jobs ? (unsigned int)(njobs_q / nwarps) : (unsigned int)njobs_q;   // claim units
+    if (threadIdx.x == 0) atomicCAS(&w.hdr[LH_STATE], 0u, 2u);       // the far pass has started (a concurrent general pass stops doubting)
+    int phase = w.hot_first ? 0 : 1;                          // 0: the units that were hot in the previous pair, 1: all others
+    unsigned int chunk_base = 0;
+    unsigned long long hotmask = 0ull;
     for (;;) {
         unsigned long long jraw = 0;
-        if (f.cta_jobs) {                                    // a CTA claims 8 adjacent strips and keeps them in lock-step:
+        unsigned int unit = 0;
+        if (phase == 0) {
+            while (hotmask == 0ull) {                         // next chunk of 64 units (every warp of a CTA sees the same mask)
+                if (f.cta_jobs) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) s_job = (unsigned long long)atomicAdd(&w.hdr[LH_HOTCLAIM], 64u);
+                    __syncthreads();
+                    chunk_base = (unsigned int)s_job;
+                } else {
+                    if (lane == 0) chunk_base = atomicAdd(&w.hdr[LH_HOTCLAIM], 64u);
+                    chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+                }
+                if (chunk_base >= nunits) break;
+                const unsigned int u0 = chunk_base + lane, u1 = u0 + 32u;
+                const unsigned int lo = __ballot_sync(0xffffffffu, u0 < nunits && w.hot_prev[u0] != 0);
+                const unsigned int hi = __ballot_sync(0xffffffffu, u1 < nunits && w.hot_prev[u1] != 0);
+                hotmask = (unsigned long long)lo | ((unsigned long long)hi << 32);
+            }
+            if (hotmask == 0ull) { phase = 1; continue; }
+            unit = chunk_base + (unsigned int)(__ffsll((long long)hotmask) - 1);
+            hotmask &= hotmask - 1ull;
+            jraw = f.cta_jobs ? (unsigned long long)unit * nwarps + warp : (unsigned long long)unit;
+        } else if (f.cta_jobs) {                             // a CTA claims 8 adjacent strips and keeps them in lock-step:
             __syncthreads();                                 // a grid row is then fetched as 8 x 224 contiguous bytes
-            if (threadIdx.x == 0) s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+            if (threadIdx.x == 0) {
+                s_job = atomicAdd(f.job_ctr, (unsigned long long)nwarps) - f.job_base;
+                s_hot = (w.hot_first && s_job < (unsigned long long)njobs_q) ? w.hot_prev[s_job / nwarps] : 0;
+            }
             __syncthreads();
             if (s_job >= (unsigned long long)njobs_q) break;
+            if (s_hot) continue;                             // done in phase 0
             jraw = s_job + (unsigned long long)warp;
+            unit = (unsigned int)(s_job / nwarps);
         } else {
-            if (lane == 0) jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
+            int hot = 0;
+            if (lane == 0) {
+                jraw = atomicAdd(f.job_ctr, 1ull) - f.job_base;
+                hot = (w.hot_first && jraw < (unsigned long long)njobs_q) ? w.hot_prev[jraw] : 0;
+            }
             jraw = __shfl_sync(0xffffffffu, jraw, 0);
+            hot = __shfl_sync(0xffffffffu, hot, 0);
             if (jraw >= (unsigned long long)njobs_q) break;
+            if (hot) continue;
+            unit = (unsigned int)jraw;
         }
         const int job = (int)jraw;
         const int strip = job - (job / nsp) * nsp;
@@ -150,6 +217,7 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
         if (strip >= f.nstrips) {                        // padding warp of a CTA job: keep the barriers company
             const int nchp = ((y1 - y0) + 8 + RB - 1) / RB;
             for (int c = 0; c < nchp; ++c) __syncthreads();
+            __syncthreads_or(0);
             continue;
         }
         const int xs = strip * F2_OUTC - F2_HALO;
@@ -279,15 +347,34 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
         }
         if (need_out) {                                  // append the row ranges that were not fully stored
             unsigned int pos = 0;
-            if (lane == 0) pos = atomicAdd(w.list_count, (unsigned int)__popc(need_out));
+            if (lane == 0) pos = atomicAdd(&w.hdr[LH_COUNT], (unsigned int)__popc(need_out));
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (lane < F2_RANGES && ((need_out >> lane) & 1u))
-                w.list[pos + __popc(need_out & ((1u << lane) - 1u))] = (sq * f.nstrips + strip) * F2_RANGES + lane;   // unpadded job numbering
+            if (lane < F2_RANGES && ((need_out >> lane) & 1u))                       // (a ticket holder polls its slot: -1 = not yet)
+                *reinterpret_cast<volatile int*>(&w.list[pos + __popc(need_out & ((1u << lane) - 1u))]) =
+                    (sq * f.nstrips + strip) * F2_RANGES + lane;                     // unpadded job numbering
+        }
+        if (f.cta_jobs) {                                // remember which units listed something: they go first in the next pair
+            const int any = __syncthreads_or(need_out != 0u);
+            if (threadIdx.x == 0) w.hot_next[unit] = (unsigned char)(any != 0);
+        } else if (lane == 0) {
+            w.hot_next[unit] = (unsigned char)(need_out != 0u);
         }
         // linked strips: the row ranges of a seam job this pass completed itself count towards the side's early publish;
         // the listed ones are counted by the general pass
         if (a.linked && (y0 < GY + 2 || y1 > a.ny - GY - 1))
             fast_seam_done(a, f, y0 < GY + 2, y1 > a.ny - GY - 1, (unsigned int)(F2_RANGES - __popc(need_out)), 2u, lane);
+    }
+    // The last warp of the grid to leave closes the list: ticket holders beyond the final count may go.  Then wait for the
+    // general pass if it runs beside this kernel (it was launched first; this kernel must not complete before it: the next
+    // launch in the stream reads what it writes).  A no-op in a plain launch.
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&w.hdr[LH_FEXITS], 1u) + 1u == gridDim.x * (unsigned int)nwarps) {
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int*>(&w.hdr[LH_FDONE]) = 1u;
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 }
 
@@ -314,6 +401,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
     const long long pitch = a.pitch;
     const uint32_t pc2b = (uint32_t)(a.step + 1ull), pc3b = (uint32_t)((a.step + 1ull) >> 32);   // level 2 = step + 1
     unsigned int gchunk = 0;
+    if (f.list_conc) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the far pass may start beside this kernel
 
     __shared__ unsigned long long s_job;
     const int nsp = f.cta_jobs ? f.nstrips_p : f.nstrips;     // strips per segment in the job numbering
@@ -328,23 +416,69 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
             if (s_job >= (unsigned long long)njobs_q) break;
             jraw = s_job + (unsigned long long)warp;
         } else if (f.list) {                                 // general pass of a far/general launch pair: the work list
+            // A warp draws a ticket and waits until the far pass has filled that slot, or has finished with fewer entries.  When
+            // this kernel follows its far pass in the stream nothing is ever waited for; launched before it (list_conc) the
+            // tickets are served while the far pass is still streaming the rest of the grid.
+            unsigned int* hdr = f.list_claim - LH_CLAIM;
             unsigned int idx = 0;
-            if (lane == 0) idx = atomicAdd(f.list_claim, 1u);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
-            if (idx >= *f.list_count) {
-                // the list is drained for this warp.  The LAST warp of the grid to get here re-arms the header for the next launch
-                // pair (count, claim, exits = 0; the count is kept in word 3 for the host's density probe): no memset per pair.
+            int entry = -1;
+            if (lane == 0) {
+                unsigned long long t0 = 0ull;
+                for (;;) {                                                   // tickets until one is served or the list is over
+                    idx = atomicAdd(f.list_claim, 1u);
+                    entry = -1;
+                    for (unsigned int spin = 1u;; ++spin) {
+                        if (idx < f.list_cap) entry = *reinterpret_cast<volatile int*>(&f.list[idx]);
+                        if (entry >= 0) break;
+                        if (ld_volatile_u32(&hdr[LH_FDONE]) != 0u) {         // far pass done: the count is final, all slots are written
+                            __threadfence();
+                            if (idx < f.list_cap) entry = *reinterpret_cast<volatile int*>(&f.list[idx]);
+                            if (entry < 0) entry = idx < ld_volatile_u32(&hdr[LH_COUNT]) ? -3 : -2;   // -3: served by an earlier launch
+                            break;
+                        }
+                        const unsigned int st = ld_volatile_u32(&hdr[LH_STATE]);
+                        if (st == 1u) { entry = -2; break; }                 // this pass gave up (below); the closing launch serves the list
+                        __nanosleep(400);
+                        if ((spin & 255u) == 0u) {
+                            // No far pass in sight for 20 ms: kernels are being serialised (a profiler, a debugger) and it cannot start
+                            // before this kernel ends.  Give up — all warps or none (the far pass moves 0 -> 2, this moves 0 -> 1).
+                            const unsigned long long now = global_timer_ns();
+                            if (t0 == 0ull) t0 = now;
+                            else if (st == 0u && now - t0 > 20000000ull) {
+                                if (atomicCAS(&hdr[LH_STATE], 0u, 1u) != 2u) { entry = -2; break; }
+                            } else if (now - t0 > 20000000000ull) {          // 20 s beside a running far pass: it is stuck
+                                atomicExch(&a.self.arrive[2], 3u);
+                                entry = -2; break;
+                            }
+                        }
+                    }
+                    // beside the far pass without `drain`: leave as soon as the far pass is done, the closing launch has the whole GPU
+                    if (entry >= 0 && f.list_conc && !f.list_drain && ld_volatile_u32(&hdr[LH_FDONE]) != 0u) entry = -2;
+                    if (entry != -3) break;
+                }
+                if (entry >= 0) *reinterpret_cast<volatile int*>(&f.list[idx]) = -1;    // slot consumed: empty for the next pair
+                else atomicMin(&hdr[LH_MIN], idx);                                       // the closing launch starts there
+            }
+            entry = __shfl_sync(0xffffffffu, entry, 0);
+            if (entry < 0) {
+                // The LAST warp of the grid to get here: a closing launch re-arms the header for the next launch pair (the count is kept
+                // for the host's density probe; no memset per pair); otherwise the tickets restart at the first unserved one.
                 if (lane == 0) {
-                    unsigned int* hdr = f.list_claim - 1;                    // [count, claim, exits, last count]
-                    if (atomicAdd(&hdr[2], 1u) + 1u == gridDim.x * (blockDim.x >> 5)) {
-                        hdr[3] = hdr[0];
-                        hdr[0] = 0u; hdr[1] = 0u; hdr[2] = 0u;
+                    if (atomicAdd(&hdr[LH_GEXITS], 1u) + 1u == gridDim.x * (blockDim.x >> 5)) {
+                        if (f.list_rearm) {
+                            hdr[LH_LAST] = hdr[LH_COUNT];
+                            hdr[LH_COUNT] = 0u; hdr[LH_CLAIM] = 0u; hdr[LH_FEXITS] = 0u; hdr[LH_FDONE] = 0u; hdr[LH_HOTCLAIM] = 0u; hdr[LH_STATE] = 0u;
+                        } else {
+                            hdr[LH_CLAIM] = hdr[LH_MIN];
+                        }
+                        hdr[LH_MIN] = 0xffffffffu;
+                        hdr[LH_GEXITS] = 0u;
                         __threadfence();
                     }
                 }
                 break;
             }
-            jraw = (unsigned long long)f.list[idx];
+            jraw = (unsigned long long)entry;
             sub = (int)(jraw & (unsigned long long)(F2_RANGES - 1));   // the far pass cuts a job into F2_RANGES row ranges:
             jraw /= F2_RANGES;                               // short jobs keep the (latency-bound) general pass short
         } else {                                             // every warp claims its own job: no barrier anywhere

@@ -292,7 +292,10 @@ class Kobayashi:
         """Sub-steps done by the single-step kernel / by two-step launch pairs, last density probe, policy mode."""
         a, b, fr, m = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_int32()
         self._ck(self._L.kob_path_stats(self._h, C.byref(a), C.byref(b), C.byref(fr), C.byref(m)))
-        return {"single_steps": int(a.value), "paired_steps": int(b.value), "dense_fraction": float(fr.value), "single_mode": bool(m.value)}
+        n = C.c_uint64()
+        self._ck(self._L.kob_concurrent_pairs(self._h, C.byref(n)))
+        return {"single_steps": int(a.value), "paired_steps": int(b.value), "dense_fraction": float(fr.value), "single_mode": bool(m.value),
+                "concurrent_pairs": int(n.value)}
 
     # ---- strips ----
     def ipc_export(self) -> bytes:

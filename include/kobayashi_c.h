@@ -178,6 +178,10 @@ int kob_launch_count(const kob_ctx* ctx, uint64_t* launches);/* kernels launched
 enum { KOB_PATH_SINGLE = 0, KOB_PATH_PAIRS = 1, KOB_PATH_ADAPTIVE = 2 };
 int kob_set_path_mode(kob_ctx* ctx, int32_t mode);
 int kob_path_stats(const kob_ctx* ctx, uint64_t* single_steps, uint64_t* paired_steps, double* dense_fraction, int32_t* single_mode);
+/* Launch pairs whose general pass ran BESIDE its far pass (programmatic dependent launch; used while the work list is short and the
+ * context has its device to itself; KOB_FAST2_CONC=0 turns it off, e.g. under a profiler that serialises kernels — the library
+ * then still gives the same results, only later).  Diagnostics; results never depend on it. */
+int kob_concurrent_pairs(const kob_ctx* ctx, uint64_t* n);
 int kob_get_dims(const kob_ctx* ctx, int64_t* nx, int64_t* ny, int64_t* ny_global, int64_t* y0);
 const char* kob_last_error(const kob_ctx* ctx);              /* ctx may be NULL: last create error */
 const char* kob_strerror(int status);

@@ -1,0 +1,26 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+T=gpurun_out/r02n
+timeout 600 python -m pytest tests/test_fast2.py -m gpu -x -q > ${T}_pytest_fast2.log 2>&1; echo "pytest rc=$?" >> ${T}_pytest_fast2.log
+tail -5 ${T}_pytest_fast2.log
+run() {
+  tag=$1; shift
+  env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-dense --no-single --no-invariance --repeats 2 > ${T}_bench_$tag.json 2> ${T}_bench_$tag.err; tail -1 ${T}_bench_$tag.err
+python - <<PY
+import json
+for l in open('${T}_bench_$tag.json'):
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); r=d['roofline']
+        print('$tag value',round(d['value'],1),[round(v,1) for v in d['repeats']['values']],'launch_ms',round(r['launch_ms'],4),'frac',round(r['frac'],3),'launches',d['gpu_launches'],'conc',r['pairs_with_concurrent_general_pass'],'listed',r['listed_range_fraction_last_probe'])
+PY
+}
+run seq KOB_FAST2_CONC=0
+run default KOB_FAST2_CONC_SM=24
+run s20 KOB_FAST2_CONC_SM=20
+run s28 KOB_FAST2_CONC_SM=28
+run s16 KOB_FAST2_CONC_SM=16
+run s24t60 KOB_FAST2_CONC_SM=24 KOB_FAST2_TICKET_US=60
+run s24t120 KOB_FAST2_CONC_SM=24 KOB_FAST2_TICKET_US=120
+run s12 KOB_FAST2_CONC_SM=12

@@ -114,3 +114,29 @@ def test_two_step_path_randomised(cg, monkeypatch):
                   noise_a=float(rng.choice([0.0, 0.01, 0.05])), anisotropy=j, theta0=theta0)
         (a, _), (b, _) = _run(cg, monkeypatch, 0, **kw), _run(cg, monkeypatch, 1, **kw)
         assert all(bit_equal(x, y) for x, y in zip(a, b)), f"case {case}: {kw}"
+
+
+@pytest.mark.parametrize("name", ["wide far field", "seam nuclei, noise, odd count", "reference default 400"])
+def test_general_pass_beside_the_far_pass_is_bit_neutral(cg, monkeypatch, name):
+    """Short work lists: the general pass is launched before its far pass and serves the list while the far pass streams the grid
+    (programmatic dependent launch, hot units first).  Same bits as the plain pair (KOB_FAST2_CONC=0) and as single steps."""
+    import gc
+    kw = dict(CASES[name])
+    kw["chunks"] = (20,) * 8                                    # kob_sync between chunks lets the probe land: later pairs run concurrently
+    gc.collect()                                                # no other live context on the device, or the library stays sequential
+    ref, _ = _run(cg, monkeypatch, 0, **kw)
+    seq, _ = _run(cg, monkeypatch, 1, env=(("KOB_FAST2_CONC", 0),), **kw)
+    monkeypatch.setenv("KOB_FAST2", "1")
+    monkeypatch.setenv("KOB_FAST2_CONC", "640")
+    g = cg.Kobayashi(kw["nx"], kw["ny"], 1e-4, kernel="fast", **{k: v for k, v in kw.items() if k not in ("nx", "ny", "nuclei", "chunks", "dense")})
+    g.clear()
+    for (x, y) in kw["nuclei"]:
+        g.add_nucleus(x, y)
+    for n in kw["chunks"]:
+        g.step(n)
+        g.sync()
+    conc, stats = g.fields(), g.path_stats()
+    g.close()
+    assert stats["concurrent_pairs"] > 0, stats
+    assert all(bit_equal(x, y) for x, y in zip(ref, seq))
+    assert all(bit_equal(x, y) for x, y in zip(ref, conc))
