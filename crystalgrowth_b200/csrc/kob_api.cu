@@ -154,6 +154,8 @@ struct kob_ctx {
     int fast2_conc = 1 << 30;
     double fast2_ticket_us = 85.0; // what a listed row range costs a warp of the general pass
     int fast2_conc_sm = 24;       // the most SMs the general pass may take from the far pass
+    int fast2_conc_margin = 100;  // per cent of the probed list length the SMs are asked for
+    int fast2_conc_thr = 160;     // per cent of fast2_conc_sm's capacity up to which the early general pass is used at all
     long long list_est = -1;      // length of the last probed work list (-1: none yet)
     bool probe_is_list = false;
     uint64_t n_conc = 0;
@@ -166,6 +168,7 @@ struct kob_ctx {
     std::string trace_path;
     std::vector<cudaEvent_t> trace_ev;
     std::vector<const char*> trace_name;
+    std::vector<long long> trace_info;
 };
 
 namespace {
@@ -180,31 +183,32 @@ int fail(kob_ctx* c, int code, const std::string& msg) {
 }
 
 // Launch trace (diagnostics): event before / after a kernel launch on the context's stream.
-inline void trace_mark(kob_ctx* c, const char* name) {
+inline void trace_mark(kob_ctx* c, const char* name, long long info = 0) {
     if (c->trace_path.empty() || c->trace_ev.size() >= 8192) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, c->stream);
     c->trace_ev.push_back(e);
     c->trace_name.push_back(name);
+    c->trace_info.push_back(info);
 }
 void trace_dump(kob_ctx* c) {
     if (c->trace_path.empty() || c->trace_ev.size() < 2) return;
     cudaStreamSynchronize(c->stream);
     if (FILE* fh = std::fopen(c->trace_path.c_str(), "w")) {
-        std::fprintf(fh, "kernel,start_us,duration_us,gap_before_us\n");
+        std::fprintf(fh, "kernel,start_us,duration_us,gap_before_us,info\n");
         float prev_end = 0.f;
         for (size_t i = 0; i + 1 < c->trace_ev.size(); i += 2) {
             float t0 = 0.f, dt = 0.f;
             cudaEventElapsedTime(&t0, c->trace_ev[0], c->trace_ev[i]);
             cudaEventElapsedTime(&dt, c->trace_ev[i], c->trace_ev[i + 1]);
-            std::fprintf(fh, "%s,%.2f,%.2f,%.2f\n", c->trace_name[i], t0 * 1e3f, dt * 1e3f, (t0 - prev_end) * 1e3f);
+            std::fprintf(fh, "%s,%.2f,%.2f,%.2f,%lld\n", c->trace_name[i], t0 * 1e3f, dt * 1e3f, (t0 - prev_end) * 1e3f, c->trace_info[i]);
             prev_end = t0 + dt;
         }
         std::fclose(fh);
     }
     for (cudaEvent_t e : c->trace_ev) cudaEventDestroy(e);
-    c->trace_ev.clear(); c->trace_name.clear();
+    c->trace_ev.clear(); c->trace_name.clear(); c->trace_info.clear();
 }
 
 #define KOB_CUDA(c, call)                                                                         \
@@ -512,18 +516,23 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         // of the general pass closes the pair (normally it finds nothing; if the kernels were serialised it does the work).
         // How many SMs: a ticket (one row range) takes a warp ~85 us; the far pass streams ~2.75 ps per cell and hardly slows down
         // while it loses up to ~1/6 of the SMs (measured at 16384^2: 24 of 148 cost it 4 %, 37 cost 13 %).  The general pass must be
-        // able to serve the whole list during the far pass — serving part of it buys nothing, the rest would still cost the closing
-        // launch one ticket time (measured) — so longer lists keep the plain far -> general order.
+        // able to serve (nearly) the whole list during the far pass — serving part of it buys nothing, the rest would still cost a
+        // full-grid closing launch one ticket time (measured) — so lists beyond 1.25 x that capacity keep the plain far -> general
+        // order.
         const double far_us = 2.75e-6 * (double)c->nx * (double)c->ny;
         const long long per_warp = std::max<long long>(1, (long long)(0.9 * far_us / c->fast2_ticket_us));
-        const long long need_sm = (std::max<long long>(c->list_est, 0) + 8 * per_warp - 1) / (8 * per_warp) + 1;
-        const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm / 4));
+        const long long est = c->list_est * c->fast2_conc_margin / 100 + 8;   // the probe is up to 16 launches old and crystals grow
+        const long long need_sm = (est + 8 * per_warp - 1) / (8 * per_warp) + 1;                                   // SMs asked for
+        const long long need_raw = (std::max<long long>(c->list_est, 0) + 8 * per_warp - 1) / (8 * per_warp) + 1;  // SMs needed as probed
+        const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm / 3));
         const bool conc = c->fast2_conc > 0 && c->list_est >= 0 && c->list_est <= c->fast2_conc && c->device < 64 &&
-                          g_ctx_on_device[c->device].load() == 1 && nsm >= 16 && 4 * need_sm <= 5 * cap_sm;
+                          g_ctx_on_device[c->device].load() == 1 && nsm >= 16 && 100 * need_raw <= (long long)c->fast2_conc_thr * cap_sm;
         const int gsm = conc ? (int)std::min<long long>(need_sm, cap_sm) : 0;
-        const bool drain = true;
+        // The early general pass leaves when the far pass is done; what it has not served by then (a stale, too small estimate)
+        // is left to the closing launch, which therefore is a full grid: never much worse than the plain order.
+        const bool drain = false;
         const int fgrid = (int)std::min<long long>((long long)(nsm - gsm) * fcps, (fjobs + FAR2_WARPS - 1) / FAR2_WARPS);
-        trace_mark(c, conc ? "pair(general || far2)" : "kob_far2");
+        trace_mark(c, conc ? "pair(general || far2)" : "kob_far2", c->list_est * 1000 + gsm);   // info: probed list length, SMs
         if (conc) {
             f.list_conc = 1; f.list_rearm = 0; f.list_drain = drain ? 1 : 0;
             kern<<<gsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
@@ -779,10 +788,16 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2")) { c->fast2 = std::min(2, std::max(0, std::atoi(e_))); c->single_mode = c->fast2 == 0; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJ")) { c->fast2_yj = c->fast2_yj_b = std::max(4, std::atoi(e_)); c->fast2_yj_env = true; }
         if (const char* e_ = std::getenv("KOB_FAST2_YJB")) c->fast2_yj_b = std::max(4, std::atoi(e_));
-        if (const char* e_ = std::getenv("KOB_TRACE")) c->trace_path = e_;
+        if (const char* e_ = std::getenv("KOB_TRACE")) {          // "%p" in the file name = process id (one file per rank)
+            c->trace_path = e_;
+            const size_t at = c->trace_path.find("%p");
+            if (at != std::string::npos) c->trace_path.replace(at, 2, std::to_string((long long)getpid()));
+        }
         if (const char* e_ = std::getenv("KOB_FAST2_CONC")) c->fast2_conc = std::max(0, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_TICKET_US")) c->fast2_ticket_us = std::max(1.0, std::atof(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_SM")) c->fast2_conc_sm = std::max(1, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_CONC_MARGIN")) c->fast2_conc_margin = std::max(50, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_CONC_THR")) c->fast2_conc_thr = std::max(50, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_LOCK")) c->fast2_lock = std::min(2, std::max(0, std::atoi(e_)));   // 0 per-warp jobs, 1 CTA jobs, 2 CTA jobs in lock-step
