@@ -375,13 +375,23 @@ def main():
             sim.step(a.substeps)
         sim.sync()
         l0, p0 = sim.launch_count, sim.path_stats()
+        w0 = sim.wait_stats() if world > 1 else None
         reps.append(timed_region())
         p1 = sim.path_stats()
+        w1 = sim.wait_stats() if world > 1 else None
         launches = sim.launch_count - l0                      # kernels launched inside ONE timed region
         paired, single = p1["paired_steps"] - p0["paired_steps"], p1["single_steps"] - p0["single_steps"]
         conc_pairs = p1["concurrent_pairs"] - p0["concurrent_pairs"]
         listed_frac = p1["dense_fraction"]
     clocks = sampler.result()
+    seam_waits = None
+    if world > 1:
+        # per rank, last repeat's timed region: how often a seam job waited for a neighbour's flag, summed waiting time of those warps
+        t = torch.tensor([w1["waits"] - w0["waits"], w1["wait_ms"] - w0["wait_ms"]], dtype=torch.float64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        seam_waits = {"per_rank_waits": [int(x[0]) for x in g], "per_rank_summed_wait_ms": [round(float(x[1]), 3) for x in g],
+                      "what": "seam jobs that found the neighbour's flag not yet published, and the summed time those warps waited, in the last timed region"}
     ms_list = [r[0] for r in reps]
     ms_med = median(ms_list)
     wall_med = median([r[1] for r in reps])
@@ -570,6 +580,8 @@ def main():
             line["shard_invariance_what"] = "2500x2063 torus, 100 sub-steps: the linked strips' gathered phi, T, theta vs one GPU, before the timed region"
         if strong is not None:
             line["strong_65536"] = strong
+        if seam_waits is not None:
+            line["seam_waits"] = seam_waits
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -502,11 +502,17 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         const long long units = ff.cta_jobs ? fjobs / FAR2_WARPS : fjobs;
         if (c->hot_units != units) {
             if (c->hot) { KOB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->hot); c->hot = nullptr; }
-            KOB_CUDA(c, cudaMalloc((void**)&c->hot, (size_t)(2 * units)));
-            KOB_CUDA(c, cudaMemsetAsync(c->hot, 0, (size_t)(2 * units), c->stream));
+            const size_t ub = ((size_t)units + 15) / 16 * 16;                              // bytes of one flag array, 16-byte aligned
+            KOB_CUDA(c, cudaMalloc((void**)&c->hot, 2 * ub + 2 * (size_t)units * sizeof(unsigned int)));   // 2 flag arrays + 2 compact lists
+            KOB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * ub + 2 * (size_t)units * sizeof(unsigned int), c->stream));
+            KOB_CUDA(c, cudaMemsetAsync(hdr + LH_HOTCNT, 0, 2 * sizeof(unsigned int), c->stream));
             c->hot_units = units;
         }
-        Far2Args w{c->worklist + HDR, hdr, c->hot + (size_t)c->hot_par * units, c->hot + (size_t)(c->hot_par ^ 1) * units, 1};
+        const size_t ub = ((size_t)units + 15) / 16 * 16;
+        unsigned int* hotlists = reinterpret_cast<unsigned int*>(c->hot + 2 * ub);
+        Far2Args w{c->worklist + HDR, hdr, c->hot + (size_t)c->hot_par * ub, c->hot + (size_t)(c->hot_par ^ 1) * ub,
+                   hotlists + (size_t)c->hot_par * units, hotlists + (size_t)(c->hot_par ^ 1) * units, c->hot_par, 1};
+        f.list_hot_par = c->hot_par;
         c->hot_par ^= 1;
         ff.job_base = c->job_expected;
         f.list = c->worklist + HDR; f.list_count = hdr + LH_COUNT; f.list_claim = hdr + LH_CLAIM;
@@ -928,8 +934,11 @@ int kob_step(kob_ctx* c, int64_t nsteps) {
     for (int64_t s = 0; s < nsteps;) {
         // Launches are queued far ahead of the GPU, and the density probe that steers the adaptive path comes back
         // asynchronously: without a bound, one long kob_step call would run entirely on the path chosen before it.  So the host
-        // never runs more than 16 launches ahead of an outstanding probe (the GPU still has those 16 queued: no bubble).
-        if (c->count_pending && c->fast2 == 2 && !c->linked && c->launches - c->probe_launch >= 16)
+        // never runs more than 16 launches ahead of an outstanding probe (the GPU still has those 16 queued: no bubble).  Linked
+        // strips that joined a ring (one process each) too — the probe sizes the early general pass there: every strip waits only
+        // for work at least 16 launches behind its own queue front, which its neighbours — stepped concurrently, at most one launch
+        // pair apart on the device — have long queued.  (Strips of one process are stepped one after the other: never block there.)
+        if (c->count_pending && c->fast2 == 2 && (!c->linked || c->ring != nullptr) && c->launches - c->probe_launch >= 16)
             KOB_CUDA(c, cudaEventSynchronize(c->ev_count));
         poll_density_probe(c);
         // KOB_FAST2 / kob_set_path_mode: 0 = single-step kernel, 1 = pairs, 2 = adaptive.  Linked strips must all run the same
@@ -1163,6 +1172,16 @@ int kob_path_stats(const kob_ctx* c, uint64_t* single_steps, uint64_t* paired_st
     if (paired_steps) *paired_steps = c->n_paired;
     if (dense_fraction) *dense_fraction = c->general_frac;
     if (single_mode) *single_mode = c->single_mode ? 1 : 0;
+    return KOB_OK;
+}
+int kob_wait_stats(kob_ctx* c, uint64_t* waits, double* wait_ms) {
+    if (!c) return KOB_ERR_INVALID_ARG;
+    KOB_TRY(set_device(c));
+    uint32_t w[2] = {0, 0};
+    KOB_CUDA(c, cudaMemcpyAsync(w, c->base + c->L.off_arrive + 16, 8, cudaMemcpyDeviceToHost, c->stream));
+    KOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (waits) *waits = w[1];
+    if (wait_ms) *wait_ms = (double)w[0] * 1.024e-3;
     return KOB_OK;
 }
 int kob_concurrent_pairs(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->n_conc; return KOB_OK; }

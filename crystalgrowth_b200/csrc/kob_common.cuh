@@ -171,6 +171,8 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, 
             __nanosleep(100);
             if (globaltimer_ns() - t0 > WAIT_TIMEOUT_NS) { atomicExch(fault, 1u); return; }
         }
+        atomicAdd(fault + 2, (uint32_t)((globaltimer_ns() - t0) >> 10));   // diagnostics (kob_wait_stats): ~us spent waiting, waits
+        atomicAdd(fault + 3, 1u);
     }
     if (sub != 0u && v != epoch && v != epoch + sub) atomicExch(fault, 2u);
 }

@@ -68,6 +68,7 @@ struct FastArgs {
     int list_drain;                // ... and stays until every listed range is served (0: leaves when the far pass is done; the
                                    // closing launch, a full grid then, serves the rest)
     int list_rearm;                // this launch is the last of the pair: its last warp re-arms the header
+    int list_hot_par;              // Far2Args::hot_par of the pair
     unsigned int* live_ctr;        // single-step kernel, probe launches only: counts the jobs that see live theta flags
     // linked strips: seam readiness is published per side as soon as the jobs touching that seam are done
     unsigned int* seam_ctr;        // [2]: low-side / high-side jobs completed in this launch (reset by the publisher)
@@ -131,6 +132,9 @@ struct FastGeom {
 #endif
 constexpr int FAST_RB = KOB_FAST_RB;     // rows per TMA chunk (= unroll of the row loop)
 static_assert(FAST_RB >= 4, "the far-field shortcut needs a chunk to cover the 4-row history of the register windows");
+#ifndef KOB_ROW_LOOP
+#define KOB_ROW_LOOP 4      // rows of a chunk per loop iteration of the row update (4: the chunk is unrolled whole)
+#endif
 constexpr int FAST_WARPS = KOB_FAST_WARPS;
 
 // an input box (4 rows x 68 columns), padded to a multiple of 128 bytes (TMA shared-memory destination alignment)
@@ -475,9 +479,8 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                 if (!skipped) {
                     // (the chunk is unrolled whole: a loop over row pairs halves the code — and the instruction-fetch stalls that
                     // small grids with short jobs show — but ptxas then spends ~50 register moves per row at the back edge)
-#pragma unroll
-                    for (int rr = 0; rr < RB; ++rr) {
-                        const int ro = rr & 1;
+                    auto one_row = [&](const int rr, auto ro_tag) {
+                        constexpr int ro = decltype(ro_tag)::value;
                         const unsigned int yrel = (unsigned int)(yrel0 + rr);       // row of pass 2, relative to y0
                         const float* prow = sp + rr * BW;
                         const float* trow = stt + rr * BW;
@@ -501,10 +504,8 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                             return fast_draw_shared(f, S, x, (uint32_t)(a.y0 + y), f.pc2, f.pc3, ro == 0, lane);
                         };
                         if (ro == 0) S.have_next = false;
-                        const bool vote = ro == 0 ? row_full<0, JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
-                                                                                          th_in, draw, np_, nt_, th2, asg)
-                                                  : row_full<1, JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
-                                                                                          th_in, draw, np_, nt_, th2, asg);
+                        const bool vote = row_full<ro, JM, NOISE != 0, ROT, GEN>(S, f.rc, f.ck, pn, prow[-1], prow[CPL], tn, trow[-1], trow[CPL],
+                                                                                 th_in, draw, np_, nt_, th2, asg);
                         if (GEN) {
                             if (store && mid_lane) {
                                 *reinterpret_cast<float2*>(obuf + rr * (OUTC * 4) + lane_out) = np_;
@@ -536,7 +537,19 @@ __global__ void __launch_bounds__(32 * FAST_WARPS, KOB_FAST_CTAS) kob_step_fast(
                             if (asg[1]) pth[1] = th2.y;
                             assigned_any |= asg[0] || asg[1];
                         }
+                    };
+#if KOB_ROW_LOOP == 2
+#pragma unroll 1
+                    for (int rp = 0; rp < RB; rp += 2) {
+                        one_row(rp, std::integral_constant<int, 0>{});
+                        one_row(rp + 1, std::integral_constant<int, 1>{});
                     }
+#else
+                    one_row(0, std::integral_constant<int, 0>{});
+                    one_row(1, std::integral_constant<int, 1>{});
+                    one_row(2, std::integral_constant<int, 0>{});
+                    one_row(3, std::integral_constant<int, 1>{});
+#endif
                 }
                 // ---- live jobs: this chunk's output boxes leave by TMA; the next chunk's input is requested ----
                 if (GEN && store) fence_async_smem();

@@ -104,17 +104,21 @@ enum : int {
     LH_GEXITS = 2,    // warps of the running general-pass launch that have left
     LH_FEXITS = 4,    // far-pass warps that have left
     LH_FDONE = 5,     // 1: the far pass is complete, LH_COUNT is final
-    LH_HOTCLAIM = 6,  // far pass, hot units first: next chunk of 64 units
+    LH_HOTCLAIM = 6,  // far pass, hot units first: next entry of the previous pair's hot list
     LH_STATE = 7,     // 0 / 1 = a general pass launched before its far pass gave up waiting for it / 2 = the far pass has started
     LH_MIN = 8,       // smallest ticket a general-pass warp left with unserved
+    LH_HOTCNT = 9,    // [2] lengths of the two hot lists (the one being read, the one being written: Far2Args::hot_par)
     LH_LAST = 12,     // count of the previous pair (host density probe)
     LH_WORDS = 16
 };
 struct Far2Args {
     int* list;                  // job ids for the general pass (-1 = empty slot)
     unsigned int* hdr;          // work-list header
-    const unsigned char* hot_prev;
+    const unsigned char* hot_prev;       // [units] 1 = the unit listed something in the previous pair
     unsigned char* hot_next;
+    const unsigned int* hotlist_prev;    // those units, compact (one claim = one unit: spread over the whole grid)
+    unsigned int* hotlist_next;
+    int hot_par;                         // hdr[LH_HOTCNT + hot_par] = length of hotlist_prev, [.. + 1 - hot_par] of hotlist_next
     int hot_first;
 };
 
@@ -159,31 +163,28 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
     const unsigned int nunits = f.cta_jobs ? (unsigned int)(njobs_q / nwarps) : (unsigned int)njobs_q;   // claim units
     if (threadIdx.x == 0) atomicCAS(&w.hdr[LH_STATE], 0u, 2u);       // the far pass has started (a concurrent general pass stops doubting)
     int phase = w.hot_first ? 0 : 1;                          // 0: the units that were hot in the previous pair, 1: all others
-    unsigned int chunk_base = 0;
-    unsigned long long hotmask = 0ull;
     for (;;) {
         unsigned long long jraw = 0;
         unsigned int unit = 0;
-        if (phase == 0) {
-            while (hotmask == 0ull) {                         // next chunk of 64 units (every warp of a CTA sees the same mask)
-                if (f.cta_jobs) {
-                    __syncthreads();
-                    if (threadIdx.x == 0) s_job = (unsigned long long)atomicAdd(&w.hdr[LH_HOTCLAIM], 64u);
-                    __syncthreads();
-                    chunk_base = (unsigned int)s_job;
-                } else {
-                    if (lane == 0) chunk_base = atomicAdd(&w.hdr[LH_HOTCLAIM], 64u);
-                    chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+        if (phase == 0) {                                     // one claim = one hot unit
+            unsigned int hi = 0;
+            if (f.cta_jobs) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const unsigned int k = atomicAdd(&w.hdr[LH_HOTCLAIM], 1u);
+                    s_job = k < w.hdr[LH_HOTCNT + w.hot_par] ? (unsigned long long)w.hotlist_prev[k] : ~0ull;
                 }
-                if (chunk_base >= nunits) break;
-                const unsigned int u0 = chunk_base + lane, u1 = u0 + 32u;
-                const unsigned int lo = __ballot_sync(0xffffffffu, u0 < nunits && w.hot_prev[u0] != 0);
-                const unsigned int hi = __ballot_sync(0xffffffffu, u1 < nunits && w.hot_prev[u1] != 0);
-                hotmask = (unsigned long long)lo | ((unsigned long long)hi << 32);
+                __syncthreads();
+                hi = (unsigned int)s_job;
+            } else {
+                if (lane == 0) {
+                    const unsigned int k = atomicAdd(&w.hdr[LH_HOTCLAIM], 1u);
+                    hi = k < w.hdr[LH_HOTCNT + w.hot_par] ? w.hotlist_prev[k] : 0xffffffffu;
+                }
+                hi = __shfl_sync(0xffffffffu, hi, 0);
             }
-            if (hotmask == 0ull) { phase = 1; continue; }
-            unit = chunk_base + (unsigned int)(__ffsll((long long)hotmask) - 1);
-            hotmask &= hotmask - 1ull;
+            if (hi >= nunits) { phase = 1; continue; }
+            unit = hi;
             jraw = f.cta_jobs ? (unsigned long long)unit * nwarps + warp : (unsigned long long)unit;
         } else if (f.cta_jobs) {                             // a CTA claims 8 adjacent strips and keeps them in lock-step:
             __syncthreads();                                 // a grid row is then fetched as 8 x 224 contiguous bytes
@@ -353,11 +354,12 @@ __global__ void __launch_bounds__(32 * FAR2_WARPS, 3) kob_far2(const __grid_cons
                 *reinterpret_cast<volatile int*>(&w.list[pos + __popc(need_out & ((1u << lane) - 1u))]) =
                     (sq * f.nstrips + strip) * F2_RANGES + lane;                     // unpadded job numbering
         }
-        if (f.cta_jobs) {                                // remember which units listed something: they go first in the next pair
-            const int any = __syncthreads_or(need_out != 0u);
-            if (threadIdx.x == 0) w.hot_next[unit] = (unsigned char)(any != 0);
-        } else if (lane == 0) {
-            w.hot_next[unit] = (unsigned char)(need_out != 0u);
+        {                                                // remember which units listed something: they go first in the next pair
+            const int any = f.cta_jobs ? __syncthreads_or(need_out != 0u) : (int)(need_out != 0u);
+            if (f.cta_jobs ? threadIdx.x == 0 : lane == 0) {
+                w.hot_next[unit] = (unsigned char)(any != 0);
+                if (any) w.hotlist_next[atomicAdd(&w.hdr[LH_HOTCNT + 1 - w.hot_par], 1u)] = unit;
+            }
         }
         // linked strips: the row ranges of a seam job this pass completed itself count towards the side's early publish;
         // the listed ones are counted by the general pass
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS, 1) kob_step_fast2(const __grid_
                         if (f.list_rearm) {
                             hdr[LH_LAST] = hdr[LH_COUNT];
                             hdr[LH_COUNT] = 0u; hdr[LH_CLAIM] = 0u; hdr[LH_FEXITS] = 0u; hdr[LH_FDONE] = 0u; hdr[LH_HOTCLAIM] = 0u; hdr[LH_STATE] = 0u;
+                            hdr[LH_HOTCNT + f.list_hot_par] = 0u;            // the hot list read in this pair is the one written in the next
                         } else {
                             hdr[LH_CLAIM] = hdr[LH_MIN];
                         }

@@ -297,6 +297,12 @@ class Kobayashi:
         return {"single_steps": int(a.value), "paired_steps": int(b.value), "dense_fraction": float(fr.value), "single_mode": bool(m.value),
                 "concurrent_pairs": int(n.value)}
 
+    def wait_stats(self) -> dict:
+        """Linked strips: seam-flag waits since creation and the summed waiting time of the warps concerned (ms)."""
+        n, ms = C.c_uint64(), C.c_double()
+        self._ck(self._L.kob_wait_stats(self._h, C.byref(n), C.byref(ms)))
+        return {"waits": int(n.value), "wait_ms": float(ms.value)}
+
     # ---- strips ----
     def ipc_export(self) -> bytes:
         h = KobIpcHandle()

@@ -182,6 +182,9 @@ int kob_path_stats(const kob_ctx* ctx, uint64_t* single_steps, uint64_t* paired_
  * context has its device to itself; KOB_FAST2_CONC=0 turns it off, e.g. under a profiler that serialises kernels — the library
  * then still gives the same results, only later).  Diagnostics; results never depend on it. */
 int kob_concurrent_pairs(const kob_ctx* ctx, uint64_t* n);
+/* Linked strips: how often a job had to wait for a neighbour's seam flag since kob_create, and the summed waiting time of those
+ * warps (several wait at once: divide by `waits` for the mean).  Synchronises the stream.  Diagnostics. */
+int kob_wait_stats(kob_ctx* ctx, uint64_t* waits, double* wait_ms);
 int kob_get_dims(const kob_ctx* ctx, int64_t* nx, int64_t* ny, int64_t* ny_global, int64_t* y0);
 const char* kob_last_error(const kob_ctx* ctx);              /* ctx may be NULL: last create error */
 const char* kob_strerror(int status);
