@@ -153,9 +153,8 @@ struct kob_ctx {
     // otherwise the largest list (row ranges) it is used for.
     int fast2_conc = 1 << 30;
     double fast2_ticket_us = 85.0; // what a listed row range costs a warp of the general pass
-    int fast2_conc_sm = 24;       // the most SMs the general pass may take from the far pass
+    int fast2_conc_sm = 1 << 20;  // the most SMs the general pass may take from the far pass (default: 40 % of the device)
     int fast2_conc_margin = 100;  // per cent of the probed list length the SMs are asked for
-    int fast2_conc_thr = 160;     // per cent of fast2_conc_sm's capacity up to which the early general pass is used at all
     long long list_est = -1;      // length of the last probed work list (-1: none yet)
     bool probe_is_list = false;
     uint64_t n_conc = 0;
@@ -518,22 +517,25 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         f.list = c->worklist + HDR; f.list_count = hdr + LH_COUNT; f.list_claim = hdr + LH_CLAIM;
         f.list_cap = (unsigned int)(F2_RANGES * njobs);
         // Short list (the last probe says so): the general pass goes FIRST, on a few SMs of its own, and serves the list while the far
-        // pass — a programmatic dependent launch, started as soon as the general pass is resident — streams the grid.  A 1-CTA launch
-        // of the general pass closes the pair (normally it finds nothing; if the kernels were serialised it does the work).
-        // How many SMs: a ticket (one row range) takes a warp ~85 us; the far pass streams ~2.75 ps per cell and hardly slows down
-        // while it loses up to ~1/6 of the SMs (measured at 16384^2: 24 of 148 cost it 4 %, 37 cost 13 %).  The general pass must be
-        // able to serve (nearly) the whole list during the far pass — serving part of it buys nothing, the rest would still cost a
-        // full-grid closing launch one ticket time (measured) — so lists beyond 1.25 x that capacity keep the plain far -> general
-        // order.
+        // pass — a programmatic dependent launch, started as soon as the general pass is resident — streams the grid.  One more
+        // launch of the general pass closes the pair (normally it finds nothing to do; it serves what a too small estimate left
+        // over, or everything if the kernels were serialised) and re-arms the list header.
+        // How many SMs g: a ticket (one listed row range) takes a warp ~85 us, so the list needs est x 85 us / (8 warps x g); the far
+        // pass streams ~2.75 ps per cell while it keeps >= ~85 % of the SMs (HBM bound: 24 of 148 SMs less cost it 4 %) and slows in
+        // proportion beyond that (37 less: 13 %; both measured at 16384^2).  Take the smallest g whose general pass finishes with
+        // the far pass; none up to 40 % of the SMs (a listed fraction of ~3 %): keep the plain far -> general order.
         const double far_us = 2.75e-6 * (double)c->nx * (double)c->ny;
-        const long long per_warp = std::max<long long>(1, (long long)(0.9 * far_us / c->fast2_ticket_us));
-        const long long est = c->list_est * c->fast2_conc_margin / 100 + 8;   // the probe is up to 16 launches old and crystals grow
-        const long long need_sm = (est + 8 * per_warp - 1) / (8 * per_warp) + 1;                                   // SMs asked for
-        const long long need_raw = (std::max<long long>(c->list_est, 0) + 8 * per_warp - 1) / (8 * per_warp) + 1;  // SMs needed as probed
-        const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm / 3));
-        const bool conc = c->fast2_conc > 0 && c->list_est >= 0 && c->list_est <= c->fast2_conc && c->device < 64 &&
-                          g_ctx_on_device[c->device].load() == 1 && nsm >= 16 && 100 * need_raw <= (long long)c->fast2_conc_thr * cap_sm;
-        const int gsm = conc ? (int)std::min<long long>(need_sm, cap_sm) : 0;
+        int gsm = 0;
+        if (c->fast2_conc > 0 && c->list_est >= 0 && c->list_est <= c->fast2_conc && c->device < 64 &&
+            g_ctx_on_device[c->device].load() == 1 && nsm >= 16) {
+            const double work_us = (double)(c->list_est * c->fast2_conc_margin / 100 + 8) * c->fast2_ticket_us / 8.0;
+            const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm * 2 / 5));
+            for (int g = 2; g <= cap_sm; ++g) {
+                const double far_g = std::max(far_us, 0.85 * far_us * nsm / (double)(nsm - g));
+                if (work_us / g <= 0.95 * far_g + 40.0) { gsm = g; break; }
+            }
+        }
+        const bool conc = gsm > 0;
         // The early general pass leaves when the far pass is done; what it has not served by then (a stale, too small estimate)
         // is left to the closing launch, which therefore is a full grid: never much worse than the plain order.
         const bool drain = false;
@@ -803,7 +805,6 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2_TICKET_US")) c->fast2_ticket_us = std::max(1.0, std::atof(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_SM")) c->fast2_conc_sm = std::max(1, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_MARGIN")) c->fast2_conc_margin = std::max(50, std::atoi(e_));
-        if (const char* e_ = std::getenv("KOB_FAST2_CONC_THR")) c->fast2_conc_thr = std::max(50, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_LOCK")) c->fast2_lock = std::min(2, std::max(0, std::atoi(e_)));   // 0 per-warp jobs, 1 CTA jobs, 2 CTA jobs in lock-step

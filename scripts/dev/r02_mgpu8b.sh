@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-8}
-T=gpurun_out/r02w${N}
+T=gpurun_out/r02zc${N}
 nvidia-smi -L > ${T}_gpus.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29541 scripts/mgpu_check.py --nx 3000 --ny 2063 --steps 120 > ${T}_check.log 2>&1
@@ -23,5 +23,5 @@ for f in ('${T}_bench_n1.json','${T}_bench.json','${T}_bench_seq.json'):
         l=l.strip()
         if l.startswith('{'):
             d=json.loads(l); r=d['roofline']
-            print(f, 'n',d['n_gpus'],'value',round(d['value'],1),[round(v,1) for v in d['repeats']['values']],'launch_ms',round(r['launch_ms'],4),'conc',r['pairs_with_concurrent_general_pass'],'launches',d['gpu_launches'], 'inv', d.get('shard_invariance'), 'strong', (d.get('strong_65536') or {}).get('value'))
+            print(f, 'n',d['n_gpus'],'value',round(d['value'],1),[round(v,1) for v in d['repeats']['values']],'launch_ms',round(r['launch_ms'],4),'conc',r['pairs_with_concurrent_general_pass'],'launches',d['gpu_launches'], 'inv', d.get('shard_invariance'), 'strong', (d.get('strong_65536') or {}).get('value'), (d.get('seam_waits') or {}).get('per_rank_waits'))
 PY
