@@ -148,11 +148,12 @@ public:
     void setSimCounters(int64_t frames, double ms) { ck(kob_set_sim_counters(ctx_, frames, ms), "kob_set_sim_counters"); }
     double simTimeMs() const { double ms = 0; ck(kob_sim_time_ms(ctx_, &ms), "kob_sim_time_ms"); return ms; }
     uint64_t launchCount() const { uint64_t n = 0; ck(kob_launch_count(ctx_, &n), "kob_launch_count"); return n; }
-    struct PathStats { uint64_t singleSteps, pairedSteps; double denseFraction; bool singleMode; };
+    struct PathStats { uint64_t singleSteps, pairedSteps; double denseFraction; bool singleMode; uint64_t concurrentPairs; };
     PathStats pathStats() const {          // which step path ran (single-step kernel / two-step launch pairs), last density probe
-        PathStats s{0, 0, 0.0, false};
+        PathStats s{0, 0, 0.0, false, 0};
         int32_t m = 0;
         ck(kob_path_stats(ctx_, &s.singleSteps, &s.pairedSteps, &s.denseFraction, &m), "kob_path_stats");
+        ck(kob_concurrent_pairs(ctx_, &s.concurrentPairs), "kob_concurrent_pairs");   // pairs whose general pass ran beside the far pass
         s.singleMode = m != 0;
         return s;
     }

@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-8}
-T=gpurun_out/r02zc${N}
+T=gpurun_out/r02ze${N}
 nvidia-smi -L > ${T}_gpus.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29541 scripts/mgpu_check.py --nx 3000 --ny 2063 --steps 120 > ${T}_check.log 2>&1
