@@ -672,3 +672,23 @@ def test_fast_tuning_variants(po, cg, monkeypatch, np_, yj, cta):
     o.step(1)
     g.step(1)
     assert max_abs(g.phi(), o.fields()[0]) <= 1e-6 and max_abs(g.t(), o.fields()[1]) <= 2e-6
+
+
+def test_launch_trace_file(cg, monkeypatch, tmp_path):
+    """KOB_TRACE=<file>: CUDA events around the step kernels' launches, written at kob_destroy (diagnostics; DESIGN §4.1b's numbers
+    come from it).  One record per launch, or per launch pair when the general pass runs beside the far pass."""
+    path = tmp_path / "trace_%p.csv"
+    monkeypatch.setenv("KOB_TRACE", str(path))
+    monkeypatch.setenv("KOB_FAST2", "1")
+    g = cg.Kobayashi(600, 400, 1e-4, kernel="fast", seed=3, noise_a=0.01)
+    g.step(20)
+    g.sync()
+    g.close()
+    import os
+    files = [f for f in os.listdir(tmp_path) if f.startswith("trace_") and f.endswith(".csv")]
+    assert len(files) == 1 and "%p" not in files[0]
+    lines = open(tmp_path / files[0]).read().strip().splitlines()
+    assert lines[0] == "kernel,start_us,duration_us,gap_before_us,info"
+    kinds = [ln.split(",")[0] for ln in lines[1:]]
+    pairs = sum(k.startswith("pair") for k in kinds) + sum(k == "kob_far2" for k in kinds)
+    assert pairs == 10 and all(float(ln.split(",")[2]) > 0 for ln in lines[1:])
