@@ -475,6 +475,27 @@ def main():
         sim.step_counter = ctr
         del saved
 
+    # ---- N > 1: the developed-field regime across the ring (BASELINE configs[4] lives there): every strip starts from the dense
+    # state of its rows and all strips run the single-step kernel (same path mode on every strip at the same sub-step) ----
+    if world > 1 and a.kernel == "fast" and a.field == "seeded" and not a.no_dense and not a.strong:
+        sim.set_fields(*dense_state(nx, ring.ny, ring.y0), np.zeros((ring.ny, nx), np.float32))
+        ring.refresh()
+        sim.set_path_mode(0)
+        sim.step(3 * a.substeps)
+        d_all = []
+        for _ in range(max(1, a.repeats)):
+            barrier()
+            ms_d = sim.step_timed(5 * a.substeps)
+            barrier()
+            d_all.append(allmax([ms_d])[0] / (5 * a.substeps))
+        sim.set_path_mode(2)
+        del_ms = median(d_all)
+        roof["dense_field"] = {"value": cells * world / (del_ms * 1e-3) / 1e9, "unit": "Gcell/s", "launch_ms": del_ms,
+                               "frac": cells * 4 * elem / (del_ms * 1e-3) / 1e9 / peak, "repeats_launch_ms": d_all,
+                               "what": f"weak scaling in the developed-field regime: every one of the {world} linked strips starts with every cell on a "
+                                       "diffuse interface and runs the single-step kernel; 30 warm-up launches, then 50 launches per repeat; "
+                                       "max over ranks; value = all strips' cell-updates / that time"}
+
     # ---- end to end through the host-buffer plugin call ----
     e2e, e2e_plugin = None, None
     if not a.no_e2e:
