@@ -155,6 +155,7 @@ struct kob_ctx {
     double fast2_ticket_us = 85.0; // what a listed row range costs a warp of the general pass
     int fast2_conc_sm = 1 << 20;  // the most SMs the general pass may take from the far pass (default: 40 % of the device)
     int fast2_conc_margin = 100;  // per cent of the probed list length the SMs are asked for
+    int fast2_conc_serial = 0;    // KOB_FAST2_CONC_SERIAL=1 (tests): serialise the early general pass and its far pass like a profiler would
     long long list_est = -1;      // length of the last probed work list (-1: none yet)
     bool probe_is_list = false;
     uint64_t n_conc = 0;
@@ -544,6 +545,7 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         if (conc) {
             f.list_conc = 1; f.list_rearm = 0; f.list_drain = drain ? 1 : 0;
             kern<<<gsm * cps, F2_WARPS * 32, smem, c->stream>>>(c->maps2, a, f);
+            if (c->fast2_conc_serial) KOB_CUDA(c, cudaStreamSynchronize(c->stream));   // test knob: what a profiler does to the pair
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)fgrid); cfg.blockDim = dim3(FAR2_WARPS * 32); cfg.dynamicSmemBytes = (size_t)far_smem; cfg.stream = c->stream;
             cudaLaunchAttribute at[1];
@@ -804,6 +806,7 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
         if (const char* e_ = std::getenv("KOB_FAST2_CONC")) c->fast2_conc = std::max(0, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_TICKET_US")) c->fast2_ticket_us = std::max(1.0, std::atof(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_SM")) c->fast2_conc_sm = std::max(1, std::atoi(e_));
+        if (const char* e_ = std::getenv("KOB_FAST2_CONC_SERIAL")) c->fast2_conc_serial = std::atoi(e_);
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_MARGIN")) c->fast2_conc_margin = std::max(50, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_FAR")) c->fast2_far = std::atoi(e_) ? 1 : 0;
         if (const char* e_ = std::getenv("KOB_FAST2_FAR_CTA")) c->fast2_far_cta = std::atoi(e_) ? 1 : 0;

@@ -140,3 +140,27 @@ def test_general_pass_beside_the_far_pass_is_bit_neutral(cg, monkeypatch, name):
     assert stats["concurrent_pairs"] > 0, stats
     assert all(bit_equal(x, y) for x, y in zip(ref, seq))
     assert all(bit_equal(x, y) for x, y in zip(ref, conc))
+
+
+def test_serialised_kernels_fall_back_to_the_closing_launch(cg, monkeypatch):
+    """Under a profiler (or a debugger) kernels are serialised: the general pass that was launched first can never see its far pass
+    start.  It gives up after 20 ms — all warps or none — and the pair's closing launch serves the whole list.  KOB_FAST2_CONC_SERIAL
+    makes the library do to itself what ncu does (a stream synchronise between the two launches); same bits, only later."""
+    import gc
+    kw = dict(CASES["seam nuclei, noise, odd count"])
+    kw["chunks"] = (6,) * 5
+    gc.collect()
+    ref, _ = _run(cg, monkeypatch, 0, **kw)
+    monkeypatch.setenv("KOB_FAST2", "1")
+    monkeypatch.setenv("KOB_FAST2_CONC_SERIAL", "1")
+    g = cg.Kobayashi(kw["nx"], kw["ny"], 1e-4, kernel="fast", seed=kw["seed"], noise_a=kw["noise_a"])
+    g.clear()
+    for (x, y) in kw["nuclei"]:
+        g.add_nucleus(x, y)
+    for n in kw["chunks"]:
+        g.step(n)
+        g.sync()
+    out, stats = g.fields(), g.path_stats()
+    g.close()
+    assert stats["concurrent_pairs"] > 0, stats
+    assert all(bit_equal(x, y) for x, y in zip(ref, out))
