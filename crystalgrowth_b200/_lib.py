@@ -66,6 +66,7 @@ SIGNATURES = {
     "kob_set_path_mode": (C.c_int, [_P, C.c_int32]),
     "kob_path_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "kob_concurrent_pairs": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "kob_policy_conc_sms": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int64]),
     "kob_wait_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "kob_get_dims": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kob_last_error": (C.c_char_p, [_P]),

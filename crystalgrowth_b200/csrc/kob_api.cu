@@ -453,6 +453,23 @@ FastArgs fast_args_of(kob_ctx* c, const StepArgs<float>& a) {
     return f;
 }
 
+// SMs for a general pass that runs beside its far pass (0: keep the plain far -> general order).  Pure host arithmetic
+// (kob_policy_conc_sms exposes it to the CPU tests): a ticket (one listed row range) takes a warp ~ticket_us, so the list needs
+// tickets x ticket_us / (8 warps x g); the far pass streams ~2.75 ps per cell while it keeps >= ~85 % of the SMs (HBM bound) and slows
+// in proportion beyond that.  The smallest g whose general pass finishes with the far pass (+40 us of slack: the closing launch
+// serves a remainder), searched up to 40 % of the device.
+int conc_sm_budget(double cells, int nsm, long long tickets, double ticket_us, int margin_pct, int cap) {
+    if (nsm < 16 || tickets < 0) return 0;
+    const double far_us = 2.75e-6 * cells;
+    const double work_us = (double)(tickets * margin_pct / 100 + 8) * ticket_us / 8.0;
+    const int cap_sm = std::max(2, std::min(cap, nsm * 2 / 5));
+    for (int g = 2; g <= cap_sm; ++g) {
+        const double far_g = std::max(far_us, 0.85 * far_us * nsm / (double)(nsm - g));
+        if (work_us / g <= 0.95 * far_g + 40.0) return g;
+    }
+    return 0;
+}
+
 // ---- two sub-steps per launch (kob_fast2.cuh) ----
 template <int JM, bool NOISE, bool ROT>
 int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
@@ -525,17 +542,10 @@ int launch_fast2_t(kob_ctx* c, const StepArgs<float>& a, FastArgs f) {
         // pass streams ~2.75 ps per cell while it keeps >= ~85 % of the SMs (HBM bound: 24 of 148 SMs less cost it 4 %) and slows in
         // proportion beyond that (37 less: 13 %; both measured at 16384^2).  Take the smallest g whose general pass finishes with
         // the far pass; none up to 40 % of the SMs (a listed fraction of ~3 %): keep the plain far -> general order.
-        const double far_us = 2.75e-6 * (double)c->nx * (double)c->ny;
         int gsm = 0;
         if (c->fast2_conc > 0 && c->list_est >= 0 && c->list_est <= c->fast2_conc && c->device < 64 &&
-            g_ctx_on_device[c->device].load() == 1 && nsm >= 16) {
-            const double work_us = (double)(c->list_est * c->fast2_conc_margin / 100 + 8) * c->fast2_ticket_us / 8.0;
-            const int cap_sm = std::max(2, std::min(c->fast2_conc_sm, nsm * 2 / 5));
-            for (int g = 2; g <= cap_sm; ++g) {
-                const double far_g = std::max(far_us, 0.85 * far_us * nsm / (double)(nsm - g));
-                if (work_us / g <= 0.95 * far_g + 40.0) { gsm = g; break; }
-            }
-        }
+            g_ctx_on_device[c->device].load() == 1)
+            gsm = conc_sm_budget((double)c->nx * (double)c->ny, nsm, c->list_est, c->fast2_ticket_us, c->fast2_conc_margin, c->fast2_conc_sm);
         const bool conc = gsm > 0;
         // The early general pass leaves when the far pass is done; what it has not served by then (a stale, too small estimate)
         // is left to the closing launch, which therefore is a full grid: never much worse than the plain order.
@@ -1187,6 +1197,9 @@ int kob_wait_stats(kob_ctx* c, uint64_t* waits, double* wait_ms) {
     if (waits) *waits = w[1];
     if (wait_ms) *wait_ms = (double)w[0] * 1.024e-3;
     return KOB_OK;
+}
+int kob_policy_conc_sms(int64_t nx, int64_t ny, int32_t sms, int64_t listed_ranges) {
+    return conc_sm_budget((double)nx * (double)ny, sms, listed_ranges, 85.0, 100, 1 << 20);
 }
 int kob_concurrent_pairs(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->n_conc; return KOB_OK; }
 int kob_launch_count(const kob_ctx* c, uint64_t* n) { if (!c || !n) return KOB_ERR_INVALID_ARG; *n = c->launches; return KOB_OK; }

@@ -182,6 +182,9 @@ int kob_path_stats(const kob_ctx* ctx, uint64_t* single_steps, uint64_t* paired_
  * context has its device to itself; KOB_FAST2_CONC=0 turns it off, e.g. under a profiler that serialises kernels — the library
  * then still gives the same results, only later).  Diagnostics; results never depend on it. */
 int kob_concurrent_pairs(const kob_ctx* ctx, uint64_t* n);
+/* The launch-pair policy as a pure function (no device needed): SMs the general pass gets beside the far pass of an nx x ny strip on
+ * a device with `sms` SMs when `listed_ranges` row ranges were listed by the last probed pair; 0 = plain far -> general order. */
+int kob_policy_conc_sms(int64_t nx, int64_t ny, int32_t sms, int64_t listed_ranges);
 /* Linked strips: how often a job had to wait for a neighbour's seam flag since kob_create, and the summed waiting time of those
  * warps (several wait at once: divide by `waits` for the mean).  Synchronises the stream.  Diagnostics. */
 int kob_wait_stats(kob_ctx* ctx, uint64_t* waits, double* wait_ms);

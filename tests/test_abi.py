@@ -71,3 +71,19 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "kob_oracle" not in txt and "libkob_oracle" not in txt, f
+
+
+def test_launch_pair_policy_is_a_pure_function(cg):
+    """How many SMs the general pass of a launch pair gets beside its far pass, without a device: grows with the
+    work list, never exceeds 40 % of the SMs, falls back to the plain far -> general order (0) for long lists and tiny devices."""
+    lib = cg.load()
+    f = lambda est, n=16384, sms=148: lib.kob_policy_conc_sms(n, n, sms, est)      # noqa: E731
+    g = [f(e) for e in (0, 100, 400, 800, 1500, 2300, 3100)]
+    assert g[0] == 2 and all(b >= a for a, b in zip(g, g[1:])), g
+    assert 18 <= f(1500) <= 26 and 36 <= f(3100) <= 50, g                          # the measured sweet spots (profiles/r02_bench_summary.md)
+    assert max(g) <= 148 * 2 // 5
+    assert f(8000) == 0 and f(10 ** 7) == 0                                        # a listed fraction beyond ~3 %: plain order
+    assert f(100, sms=8) == 0                                                       # not worth it on a sliver of a device
+    assert f(-1) == 0                                                               # no probe yet
+    # a small grid: the far pass is short, a ticket does not fit beside it more than once per warp
+    assert f(50, n=4096) >= 1 and f(5000, n=4096) == 0
