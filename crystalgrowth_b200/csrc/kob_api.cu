@@ -813,6 +813,13 @@ int kob_create(kob_ctx** out, int64_t nx, int64_t ny, const kob_params* params, 
             const size_t at = c->trace_path.find("%p");
             if (at != std::string::npos) c->trace_path.replace(at, 2, std::to_string((long long)getpid()));
         }
+        // A CUDA tool injected into this process is likely to serialise kernels (ncu sets NV_COMPUTE_PROFILER_PERFWORKS_DIR and
+        // NV_NSIGHT_INJECTION_PORT_BASE in its target; other tools come in through CUDA_INJECTION64_PATH): keep the plain
+        // far -> general order then, instead of letting every early general pass wait 20 ms for a far pass that cannot start.
+        // An explicit KOB_FAST2_CONC wins; if a tool is not recognised the 20 ms fallback still gives the right answer.
+        if (std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || std::getenv("NV_NSIGHT_INJECTION_PORT_BASE") ||
+            std::getenv("CUDA_INJECTION64_PATH"))
+            c->fast2_conc = 0;
         if (const char* e_ = std::getenv("KOB_FAST2_CONC")) c->fast2_conc = std::max(0, std::atoi(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_TICKET_US")) c->fast2_ticket_us = std::max(1.0, std::atof(e_));
         if (const char* e_ = std::getenv("KOB_FAST2_CONC_SM")) c->fast2_conc_sm = std::max(1, std::atoi(e_));
