@@ -9,7 +9,11 @@ src/Kobayashi.cpp:241-249).  Same byte layout as Kobayashi::saveCheckpoint in in
     256 phi, T, theta: ny*nx elements each, reference layout i + nx*j
 
 The functions here are pure host code (numpy); `Kobayashi.save_checkpoint/load_checkpoint` move the state to and
-from the device through kob_get_fields / kob_set_fields / kob_set_params / kob_set_step_counter.
+from the device through kob_get_fields / kob_set_fields / kob_set_params / kob_set_step_counter / kob_set_sim_counters.
+
+Not in the file: a host-injected noise field (kob_set_noise_field) — it is an input the caller owns and passes again after a
+resume; the built-in Philox noise needs nothing beyond the seed and the step counter.  A ring resume is one file per strip plus
+the ring-wide halo refresh (`StripRing.load_checkpoint`).
 """
 from __future__ import annotations
 
