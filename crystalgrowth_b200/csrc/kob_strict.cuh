@@ -18,6 +18,14 @@
 
 namespace kob {
 
+// x / d for d > 0 (dx, dy, 3 dx^2, tau: validated at kob_create): a zero numerator — the far field, where this kernel spends most of
+// its launches — gives the zero back with its sign, which is exactly what the correctly rounded division returns; everything else
+// goes through it.  Same bits, ~10 instructions less per division on rows without crystal.
+template <typename real>
+__device__ __forceinline__ real div_pos(real x, real d) { return x == (real)0 ? x : rn_div(x, d); }
+__device__ __forceinline__ bool is_plus_zero(float v) { return __float_as_uint(v) == 0u; }
+__device__ __forceinline__ bool is_plus_zero(double v) { return __double_as_longlong(v) == 0ll; }
+
 template <typename real, int TX, int TY, bool NOISE>
 __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
     constexpr int PW = TX + 4, PH = TY + 4;   // phi tile
@@ -59,6 +67,17 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
     }
     __syncthreads();
     const bool theta_live = s_flag != 0u;
+    // eps, eps' of a cell that holds theta = +0 (every cell that never saw an interface): the same expressions as below on the
+    // same input, evaluated once per thread instead of once per cell
+    real eps0, epsd0;
+    {
+        const real th0 = (real)0;
+        const real arg0 = (P.theta0 == (real)0) ? rn_mul(P.aniso, th0) : rn_mul(P.aniso, rn_sub(th0, P.theta0));
+        real sn0, cs0;
+        p_sincos_core(arg0, &sn0, &cs0);
+        eps0 = rn_mul(P.epsbar, rn_add((real)1.0f, rn_mul(P.delta, cs0)));
+        epsd0 = rn_mul(P.neg_ebjd, sn0);
+    }
 
     // ---- stage 1: pass 1 on the ring (src/Kobayashi.cpp:139-171) ----
     const real e = (real)REF_DEADBAND;
@@ -68,8 +87,8 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         const int ry = k / RW, rx = k - ry * RW;     // ring coordinates; cell = (x0-1+rx, y0-1+ry)
         const int px = rx + 1, py = ry + 1;          // same cell in the phi tile
         const int ci = x0 - 1 + rx, cj = y0 - 1 + ry;
-        const real gx = rn_div(rn_sub(s_phi[py][px + 1], s_phi[py][px - 1]), P.dx);   // :139
-        const real gy = rn_div(rn_sub(s_phi[py + 1][px], s_phi[py - 1][px]), P.dy);   // :140
+        const real gx = div_pos(rn_sub(s_phi[py][px + 1], s_phi[py][px - 1]), P.dx);   // :139
+        const real gy = div_pos(rn_sub(s_phi[py + 1][px], s_phi[py - 1][px]), P.dy);   // :140
         // angle state machine :154-167
         const bool gx_flat = (gx <= e) && (gx >= -e);
         const bool gy_neg = gy < -e, gy_pos = gy > e;
@@ -92,11 +111,16 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         } else if (theta_live && in_grid) {
             th = a.self.theta[pidx<real>(pitch, ci, cj)];   // held: keep last angle
         }
-        const real arg = (P.theta0 == (real)0) ? rn_mul(P.aniso, th) : rn_mul(P.aniso, rn_sub(th, P.theta0));
-        real sn, cs;
-        p_sincos_core(arg, &sn, &cs);
-        s_eps[ry][rx] = rn_mul(P.epsbar, rn_add((real)1.0f, rn_mul(P.delta, cs)));   // :170
-        s_epsd[ry][rx] = rn_mul(P.neg_ebjd, sn);                                      // :171
+        if (is_plus_zero(th)) {
+            s_eps[ry][rx] = eps0;
+            s_epsd[ry][rx] = epsd0;
+        } else {
+            const real arg = (P.theta0 == (real)0) ? rn_mul(P.aniso, th) : rn_mul(P.aniso, rn_sub(th, P.theta0));
+            real sn, cs;
+            p_sincos_core(arg, &sn, &cs);
+            s_eps[ry][rx] = rn_mul(P.epsbar, rn_add((real)1.0f, rn_mul(P.delta, cs)));   // :170
+            s_epsd[ry][rx] = rn_mul(P.neg_ebjd, sn);                                      // :171
+        }
         s_gx[ry][rx] = gx;
         s_gy[ry][rx] = gy;
     }
@@ -123,7 +147,7 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         lp = rn_add(lp, s_phi[py + 1][px - 1]);
         lp = rn_add(lp, s_phi[py - 1][px + 1]);
         const real op = s_phi[py][px];
-        lp = rn_div(rn_sub(lp, rn_mul((real)12.0f, op)), P.lapden);
+        lp = div_pos(rn_sub(lp, rn_mul((real)12.0f, op)), P.lapden);
         const real tE = s_t[ry][rx + 1], tW = s_t[ry][rx - 1], tN = s_t[ry + 1][rx], tS = s_t[ry - 1][rx];
         real lt = rn_mul((real)2.0f, rn_add(rn_add(rn_add(tE, tW), tN), tS));
         lt = rn_add(lt, s_t[ry + 1][rx + 1]);
@@ -131,14 +155,14 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         lt = rn_add(lt, s_t[ry + 1][rx - 1]);
         lt = rn_add(lt, s_t[ry - 1][rx + 1]);
         const real ot = s_t[ry][rx];
-        lt = rn_div(rn_sub(lt, rn_mul((real)12.0f, ot)), P.lapden);
+        lt = div_pos(rn_sub(lt, rn_mul((real)12.0f, ot)), P.lapden);
 
         const real eC = s_eps[ry][rx], eE = s_eps[ry][rx + 1], eW = s_eps[ry][rx - 1], eN = s_eps[ry + 1][rx], eS = s_eps[ry - 1][rx];
-        const real gepx = rn_div(rn_sub(rn_mul(eE, eE), rn_mul(eW, eW)), P.dx);           // :190-192
-        const real gepy = rn_div(rn_sub(rn_mul(eN, eN), rn_mul(eS, eS)), P.dy);           // :193-195
-        const real term1 = rn_div(rn_sub(rn_mul(rn_mul(eN, s_epsd[ry + 1][rx]), s_gx[ry + 1][rx]),
+        const real gepx = div_pos(rn_sub(rn_mul(eE, eE), rn_mul(eW, eW)), P.dx);           // :190-192
+        const real gepy = div_pos(rn_sub(rn_mul(eN, eN), rn_mul(eS, eS)), P.dy);           // :193-195
+        const real term1 = div_pos(rn_sub(rn_mul(rn_mul(eN, s_epsd[ry + 1][rx]), s_gx[ry + 1][rx]),
                                          rn_mul(rn_mul(eS, s_epsd[ry - 1][rx]), s_gx[ry - 1][rx])), P.dy);   // :197-199
-        const real term2 = rn_div(-rn_sub(rn_mul(rn_mul(eE, s_epsd[ry][rx + 1]), s_gy[ry][rx + 1]),
+        const real term2 = div_pos(-rn_sub(rn_mul(rn_mul(eE, s_epsd[ry][rx + 1]), s_gy[ry][rx + 1]),
                                           rn_mul(rn_mul(eW, s_epsd[ry][rx - 1]), s_gy[ry][rx - 1])), P.dx);  // :201-203
         const real term3 = rn_add(rn_mul(gepx, s_gx[ry][rx]), rn_mul(gepy, s_gy[ry][rx]));                   // :204
         const real m = rn_mul(P.alpha_over_pi, p_atan(rn_mul(P.gamma, rn_sub(P.teq, ot))));                  // :206
@@ -155,7 +179,7 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
                 sum = rn_add(sum, rn_mul(rn_mul(P.noise_a, q), rn_sub((real)r, (real)0.5f)));
             }
         }
-        const real np = rn_add(op, rn_div(rn_mul(sum, P.dt), P.tau));                                        // :211,214
+        const real np = rn_add(op, div_pos(rn_mul(sum, P.dt), P.tau));                                        // :211,214
         const real nt = rn_add(rn_add(ot, rn_mul(lt, P.dt)), rn_mul(P.K, rn_sub(np, op)));                   // :215
         store_aliases<real>(phi_out, phi_lo, phi_hi, pitch, a.nx, a.ny, a.lower.ny, i, j, np);
         store_aliases<real>(t_out, t_lo, t_hi, pitch, a.nx, a.ny, a.lower.ny, i, j, nt);
