@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         eps0 = rn_mul(P.epsbar, rn_add((real)1.0f, rn_mul(P.delta, cs0)));
         epsd0 = rn_mul(P.neg_ebjd, sn0);
     }
+    // m(T) of a cell whose temperature is still exactly +0 (far from every crystal): :206 on that input, once per thread
+    const real m0 = rn_mul(P.alpha_over_pi, p_atan(rn_mul(P.gamma, rn_sub(P.teq, (real)0))));
 
     // ---- stage 1: pass 1 on the ring (src/Kobayashi.cpp:139-171) ----
     const real e = (real)REF_DEADBAND;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) kob_step_strict(const StepArgs<real> a) {
         const real term2 = div_pos(-rn_sub(rn_mul(rn_mul(eE, s_epsd[ry][rx + 1]), s_gy[ry][rx + 1]),
                                           rn_mul(rn_mul(eW, s_epsd[ry][rx - 1]), s_gy[ry][rx - 1])), P.dx);  // :201-203
         const real term3 = rn_add(rn_mul(gepx, s_gx[ry][rx]), rn_mul(gepy, s_gy[ry][rx]));                   // :204
-        const real m = rn_mul(P.alpha_over_pi, p_atan(rn_mul(P.gamma, rn_sub(P.teq, ot))));                  // :206
+        const real m = is_plus_zero(ot) ? m0 : rn_mul(P.alpha_over_pi, p_atan(rn_mul(P.gamma, rn_sub(P.teq, ot))));   // :206
         const real q = rn_mul(op, rn_sub((real)1.0f, op));
         real sum = rn_add(term1, term2);
         sum = rn_add(sum, rn_mul(rn_mul(eC, eC), lp));
